@@ -1,0 +1,658 @@
+// exenv_api.cu -- the C ABI (include/exenv_b200.h): plan management, argument validation, the host-side emulation of
+// diffrax.diffeqsolve's time bookkeeping (build_schedule) and the host-buffer pipeline used for end-to-end numbers.
+// No CPU compute fallback exists: every compute entry point needs a CUDA device and launches the sm_100a kernels of
+// exenv_step.cu / exenv_sim.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "exenv_internal.h"
+
+namespace exenv {
+
+static thread_local char g_err[512] = {0};
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define EX_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess) {                                                 \
+      set_error("%s failed: %s", #call, cudaGetErrorString(e_));             \
+      return EXENV_ERR_CUDA;                                                 \
+    }                                                                        \
+  } while (0)
+
+static const ExenvDims kDims[6] = {
+    /* pendulum   */ {2, 2, 1, 2, 3, 2},
+    /* msd        */ {2, 2, 1, 2, 3, 2},
+    /* fluid tank */ {1, 1, 1, 1, 4, 1},
+    /* cart pole  */ {4, 4, 1, 4, 6, 4},
+    /* acrobot    */ {4, 4, 1, 4, 9, 4},
+    /* pmsm       */ {7, 3, 2, 8, 7, 1},
+};
+
+// ---- diffeqsolve time bookkeeping, emulated in the solve dtype T --------------------------------------------------
+// Restates (diffrax==0.7.0 is not vendored by the reference):
+//   t1 = action_stepsize * n_actions; ts = jnp.linspace(0, t1, 1 + int(t1 / obs_stepsize))   (pendulum_env.py:222-225)
+//   tprev = 0; tnext = clip_to_end(0 + dt0)
+//   while tprev < t1: step over [tprev, tnext]; save every ts[i] <= tnext by dense output over [tprev, tnext];
+//                     tprev' = min(tnext, t1); tnext' = clip_to_end(tnext + dt0)   (ConstantStepSize, dt0 = obs_stepsize)
+//   stage i of the solver evaluates the ZOH closure at tprev + c_i * (tnext - tprev):
+//                     index = int(t / action_stepsize), clamped to the last action (pendulum_env.py:215-216)
+// Everything is plain IEEE arithmetic in T (this file is compiled with -ffp-contract=off).
+template <typename T>
+static int build_schedule_t(const ExenvPlan &plan, int64_t n_actions, double obs_dt_d, double act_dt_d,
+                            int tile_steps, SimSchedule &out) {
+  const bool tsit = plan.desc.solver == EXENV_TSIT5;
+  const bool pmsm = plan.desc.env == EXENV_PMSM;
+  if (!(obs_dt_d > 0) || !(act_dt_d > 0) || n_actions < 1) {
+    set_error("sim_ahead: step sizes must be positive and n_actions >= 1");
+    return EXENV_ERR_INVALID;
+  }
+  const double t1_d = act_dt_d * (double)n_actions;
+  const int64_t N = (int64_t)(t1_d / obs_dt_d);
+  if (N < 1 || N > (int64_t)1 << 30) {
+    set_error("sim_ahead: unsupported number of saved samples %lld", (long long)(N + 1));
+    return EXENV_ERR_INVALID;
+  }
+  const T t1 = (T)t1_d, dt0 = (T)obs_dt_d, adt = (T)act_dt_d;
+  const T tol = sizeof(T) == 8 ? (T)1e-10 : (T)1e-6;
+  auto clip_to_end = [&](T tn) -> T { return (tn > t1 - tol) ? t1 : tn; };
+  std::vector<T> ts((size_t)N + 1);
+  for (int64_t i = 0; i < N; ++i) {
+    const T s = (T)i / (T)N;
+    ts[(size_t)i] = (T)0 * ((T)1 - s) + t1 * s;
+  }
+  ts[(size_t)N] = t1;
+  static const double c_d[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+
+  out = SimSchedule();
+  out.n_actions = n_actions;
+  out.n_save = N + 1;
+  T tprev = (T)0, tnext = clip_to_end((T)0 + dt0);
+  int64_t si = 0;
+  const int64_t hard_cap = 4 * (N + 8);
+  std::vector<int> save_count;
+  while (tprev < t1) {
+    if ((int64_t)out.words.size() > hard_cap) {
+      set_error("sim_ahead: the emulated solver loop does not terminate (dt0 too small for the dtype?)");
+      return EXENV_ERR_INVALID;
+    }
+    const T dt = tnext - tprev;
+    int64_t idx[7];
+    const int n_st = tsit ? 7 : 1;
+    for (int s = 0; s < 7; ++s) {
+      if (s < n_st) {
+        const T ti = tprev + (T)c_d[s] * dt;
+        int64_t q = (int64_t)(ti / adt);
+        if (q < 0) q = 0;
+        if (q > n_actions - 1) q = n_actions - 1;
+        idx[s] = q;
+      } else {
+        idx[s] = idx[0];
+      }
+    }
+    int64_t base = idx[0];
+    for (int s = 1; s < 7; ++s) base = std::min(base, idx[s]);
+    uint64_t w = (uint64_t)(uint32_t)base;
+    for (int s = 0; s < 7; ++s) {
+      const int64_t d = idx[s] - base;
+      if (d > 3) {
+        set_error("sim_ahead: a solver step spans more than 4 action intervals (obs_stepsize > action_stepsize?)");
+        return EXENV_ERR_UNSUPPORTED;
+      }
+      w |= (uint64_t)d << (32 + 2 * s);
+    }
+    int ns = 0;
+    while (si <= N && ts[(size_t)si] <= tnext) {
+      const T th = (tprev == tnext) ? (T)0 : (ts[(size_t)si] - tprev) / (tnext - tprev);
+      out.theta.push_back((double)th);
+      ++si;
+      ++ns;
+    }
+    if (ns > 15) {
+      set_error("sim_ahead: more than 15 saves inside one solver step");
+      return EXENV_ERR_UNSUPPORTED;
+    }
+    w |= (uint64_t)ns << 46;
+    out.words.push_back(w);
+    out.dt.push_back((double)dt);
+    save_count.push_back(ns);
+    T ntprev = tnext;
+    T ntnext = plan.desc.time_rule ? tnext + (tnext - tprev) : tnext + dt0;
+    if (ntprev > t1) ntprev = t1;
+    ntnext = clip_to_end(ntnext);
+    tprev = ntprev;
+    tnext = ntnext;
+  }
+  out.n_steps = (int64_t)out.words.size();
+  if (si != N + 1) {
+    set_error("sim_ahead: internal error, %lld of %lld samples scheduled", (long long)si, (long long)(N + 1));
+    return EXENV_ERR_INVALID;
+  }
+
+  // ---- tiles
+  out.tile_steps = tile_steps;
+  int64_t save_run = 0;
+  for (int64_t n0 = 0; n0 < out.n_steps; n0 += tile_steps) {
+    SimTile t{};
+    t.step_begin = (int)n0;
+    t.step_count = (int)std::min<int64_t>(tile_steps, out.n_steps - n0);
+    int64_t lo = INT64_MAX, hi = -1;
+    int sc = 0;
+    for (int n = t.step_begin; n < t.step_begin + t.step_count; ++n) {
+      const uint64_t w = out.words[(size_t)n];
+      const int64_t base = (int64_t)(w & 0xffffffffull);
+      int64_t mx = base;
+      for (int s = 0; s < 7; ++s) mx = std::max(mx, base + (int64_t)((w >> (32 + 2 * s)) & 3));
+      lo = std::min(lo, base);
+      hi = std::max(hi, mx);
+      sc += save_count[(size_t)n];
+    }
+    t.save_begin = (int)save_run;
+    t.save_cnt = sc;
+    if (pmsm && plan.deadtime > 0 && sc > 0) {  // buffer leaves of the saved states index the same staged sequence
+      lo = std::min<int64_t>(lo, save_run);
+      hi = std::max<int64_t>(hi, save_run + sc - 1);
+    }
+    const bool is_last = n0 + tile_steps >= out.n_steps;
+    if (is_last) hi = std::max<int64_t>(hi, n_actions - 1);  // solver.init at t1 reads the clamped last action
+    save_run += sc;
+    t.act_lo = (int)lo;
+    t.act_cnt = (int)(hi - lo + 1);
+    out.act_cap = std::max(out.act_cap, t.act_cnt);
+    out.save_cap = std::max(out.save_cap, t.save_cnt);
+    out.tiles.push_back(t);
+  }
+  out.n_tiles = (int)out.tiles.size();
+  if (out.save_cap < 1) out.save_cap = 1;
+  return EXENV_OK;
+}
+
+static int upload_schedule(const ExenvPlan &plan, SimSchedule &s) {
+  const bool f64 = plan.desc.dtype == EXENV_F64;
+  const size_t es = f64 ? 8 : 4;
+  EX_CUDA(cudaMalloc(&s.d_words, s.words.size() * sizeof(uint64_t)));
+  EX_CUDA(cudaMalloc(&s.d_dt, s.dt.size() * es));
+  EX_CUDA(cudaMalloc(&s.d_theta, std::max<size_t>(1, s.theta.size()) * es));
+  EX_CUDA(cudaMalloc(&s.d_tiles, s.tiles.size() * sizeof(SimTile)));
+  EX_CUDA(cudaMemcpy(s.d_words, s.words.data(), s.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  EX_CUDA(cudaMemcpy(s.d_tiles, s.tiles.data(), s.tiles.size() * sizeof(SimTile), cudaMemcpyHostToDevice));
+  if (f64) {
+    EX_CUDA(cudaMemcpy(s.d_dt, s.dt.data(), s.dt.size() * 8, cudaMemcpyHostToDevice));
+    EX_CUDA(cudaMemcpy(s.d_theta, s.theta.data(), s.theta.size() * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> a(s.dt.begin(), s.dt.end()), b(s.theta.begin(), s.theta.end());
+    EX_CUDA(cudaMemcpy(s.d_dt, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+    EX_CUDA(cudaMemcpy(s.d_theta, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return EXENV_OK;
+}
+
+static void free_schedule(SimSchedule &s) {
+  cudaFree(s.d_words);
+  cudaFree(s.d_dt);
+  cudaFree(s.d_theta);
+  cudaFree(s.d_tiles);
+  s.d_words = nullptr;
+  s.d_dt = s.d_theta = nullptr;
+  s.d_tiles = nullptr;
+}
+
+static int build_schedule(const ExenvPlan &plan, int64_t n_actions, double obs_dt, double act_dt, int tile_steps,
+                          SimSchedule &out) {
+  return plan.desc.dtype == EXENV_F64 ? build_schedule_t<double>(plan, n_actions, obs_dt, act_dt, tile_steps, out)
+                                      : build_schedule_t<float>(plan, n_actions, obs_dt, act_dt, tile_steps, out);
+}
+
+// Tile length: as many solver steps as fit the per-CTA shared-memory share that keeps >= 16 warps per SM resident.
+static int auto_tile_steps(const ExenvPlan &plan, int E) {
+  const size_t sm_total = 227 * 1024;
+  int ctas = std::max(1, 512 / E);
+  if (plan.desc.dtype == EXENV_F64 && ctas > 1) ctas = std::max(1, 384 / E);
+  const size_t budget = sm_total / ctas - 1024;
+  const int cand[] = {64, 48, 32, 24, 16, 12, 8, 4, 2, 1};
+  for (int k : cand)
+    if (sim_smem_bytes(plan, E, k + 3, k + 1) <= budget) return k;
+  return 1;
+}
+
+static int get_schedule(ExenvPlan *plan, int64_t n_actions, double obs_dt, double act_dt, int tile_steps,
+                        bool need_device, SimSchedule **out) {
+  std::lock_guard<std::mutex> lock(plan->mu);
+  auto key = std::make_tuple(n_actions, obs_dt, act_dt, tile_steps);
+  auto it = plan->schedules.find(key);
+  if (it == plan->schedules.end()) {
+    SimSchedule s;
+    int rc = build_schedule(*plan, n_actions, obs_dt, act_dt, tile_steps, s);
+    if (rc != EXENV_OK) return rc;
+    it = plan->schedules.emplace(key, std::move(s)).first;
+  }
+  if (need_device && !it->second.d_words) {
+    EX_CUDA(cudaSetDevice(plan->device));
+    int rc = upload_schedule(*plan, it->second);
+    if (rc != EXENV_OK) return rc;
+  }
+  *out = &it->second;
+  return EXENV_OK;
+}
+
+static bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace exenv
+
+using namespace exenv;
+
+extern "C" {
+
+int exenv_abi_version(void) { return EXENV_ABI_VERSION; }
+
+size_t exenv_last_error(char *buf, size_t cap) {
+  const size_t n = strlen(g_err);
+  if (buf && cap) {
+    const size_t m = std::min(n, cap - 1);
+    memcpy(buf, g_err, m);
+    buf[m] = 0;
+  }
+  return n;
+}
+
+int exenv_env_dims(int32_t env, ExenvDims *out) {
+  if (env < 0 || env > 5 || !out) {
+    set_error("exenv_env_dims: bad env id %d", env);
+    return EXENV_ERR_INVALID;
+  }
+  *out = kDims[env];
+  return EXENV_OK;
+}
+
+uint64_t exenv_launch_count(void) { return g_launch_count.load(); }
+
+int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
+  if (!desc || !out) {
+    set_error("exenv_plan_create: NULL argument");
+    return EXENV_ERR_NULL;
+  }
+  if (desc->env < 0 || desc->env > 5 || (desc->solver != EXENV_EULER && desc->solver != EXENV_TSIT5) ||
+      (desc->dtype != EXENV_F32 && desc->dtype != EXENV_F64)) {
+    set_error("exenv_plan_create: bad env/solver/dtype (%d, %d, %d)", desc->env, desc->solver, desc->dtype);
+    return EXENV_ERR_INVALID;
+  }
+  const ExenvDims dm = kDims[desc->env];
+  if (desc->n_control < 0 || desc->n_control > EXENV_MAX_CONTROL) {
+    set_error("exenv_plan_create: n_control out of range");
+    return EXENV_ERR_INVALID;
+  }
+  for (int j = 0; j < desc->n_control; ++j)
+    if (desc->control[j] < 0 || desc->control[j] >= dm.n_phys) {
+      set_error("exenv_plan_create: control_state index %d is not a PhysicalState field", desc->control[j]);
+      return EXENV_ERR_INVALID;
+    }
+  if (!(desc->tau > 0)) {
+    set_error("exenv_plan_create: tau must be positive");
+    return EXENV_ERR_INVALID;
+  }
+  const bool sat = desc->flags & EXENV_FLAG_SATURATED;
+  if (sat && desc->env != EXENV_PMSM) {
+    set_error("exenv_plan_create: the saturated flag is only valid for PMSM");
+    return EXENV_ERR_INVALID;
+  }
+  ExenvPlan *p = new (std::nothrow) ExenvPlan();
+  if (!p) return EXENV_ERR_NOMEM;
+  p->desc = *desc;
+  p->dims = dm;
+  p->dims.n_trunc = (desc->env == EXENV_FLUID_TANK || desc->env == EXENV_PMSM) ? 1 : dm.n_obs + desc->n_control;
+  p->device = device;
+  const int np = dm.n_static + 2 * dm.n_phys + 2 * dm.n_act;
+  for (int i = 0; i < np; ++i) p->per_env |= desc->pp[i] != nullptr;
+  for (int i = np; i < EXENV_MAX_PARAMS; ++i) p->desc.pp[i] = nullptr;
+  if (desc->env == EXENV_PMSM) {
+    if (p->per_env) {  // the reference hashes PMSM env_properties as a static jit argument (pmsm_env.py:525, :851)
+      set_error("PMSM does not support per-environment parameter arrays");
+      delete p;
+      return EXENV_ERR_UNSUPPORTED;
+    }
+    const double dead = desc->p[6];
+    p->deadtime = (int)dead;
+    p->pmsm_adv = (dead + 0.5) * desc->tau;
+    if (p->deadtime < 0 || p->deadtime > 1) {
+      set_error("PMSM deadtime must be 0 or 1 (the reference's buffers hold one action)");
+      delete p;
+      return EXENV_ERR_UNSUPPORTED;
+    }
+  }
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    set_error("exenv_plan_create: no usable CUDA device %d (%s); this library has no CPU fallback", device,
+              cudaGetErrorString(ce));
+    delete p;
+    return EXENV_ERR_CUDA;
+  }
+  if (sat) {
+    if (!desc->lut_gx || !desc->lut_gy || !desc->lut_maps || desc->lut_nx < 2 || desc->lut_ny < 2) {
+      set_error("saturated PMSM needs lut_gx / lut_gy / lut_maps");
+      delete p;
+      return EXENV_ERR_NULL;
+    }
+    const int nx = desc->lut_nx, ny = desc->lut_ny;
+    const size_t es = desc->dtype == EXENV_F64 ? 8 : 4;
+    auto pad16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
+    DevLut &L = p->lut;
+    L.nx = nx;
+    L.ny = ny;
+    L.off_gy = pad16((size_t)nx * es);
+    L.off_cells = L.off_gy + pad16((size_t)ny * es);
+    L.bytes = L.off_cells + pad16((size_t)nx * ny * 6 * es);
+    L.inv_dx = 1.0 / (desc->lut_gx[1] - desc->lut_gx[0]);
+    L.inv_dy = 1.0 / (desc->lut_gy[1] - desc->lut_gy[0]);
+    std::vector<unsigned char> blob(L.bytes, 0);
+    auto put = [&](size_t off, size_t i, double v) {
+      if (es == 8)
+        reinterpret_cast<double *>(blob.data() + off)[i] = v;
+      else
+        reinterpret_cast<float *>(blob.data() + off)[i] = (float)v;
+    };
+    for (int i = 0; i < nx; ++i) put(0, (size_t)i, desc->lut_gx[i]);
+    for (int j = 0; j < ny; ++j) put(L.off_gy, (size_t)j, desc->lut_gy[j]);
+    for (int q = 0; q < 6; ++q)
+      for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+          put(L.off_cells, ((size_t)i * ny + j) * 6 + q, desc->lut_maps[((size_t)q * nx + i) * ny + j]);
+    if (cudaMalloc(&L.blob, L.bytes) != cudaSuccess ||
+        cudaMemcpy(L.blob, blob.data(), L.bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("exenv_plan_create: LUT upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      delete p;
+      return EXENV_ERR_CUDA;
+    }
+    p->desc.lut_gx = p->desc.lut_gy = p->desc.lut_maps = nullptr;  // host pointers are not retained
+  }
+  *out = p;
+  return EXENV_OK;
+}
+
+int exenv_plan_destroy(exenv_plan_t plan) {
+  if (!plan) return EXENV_OK;
+  cudaSetDevice(plan->device);
+  for (auto &kv : plan->schedules) free_schedule(kv.second);
+  if (plan->lut.blob) cudaFree(plan->lut.blob);
+  delete plan;
+  return EXENV_OK;
+}
+
+int exenv_step(exenv_plan_t plan, const ExenvStepArgs *a, void *stream) {
+  if (!plan || !a) {
+    set_error("exenv_step: NULL plan/args");
+    return EXENV_ERR_NULL;
+  }
+  if (a->batch < 0) {
+    set_error("exenv_step: negative batch");
+    return EXENV_ERR_INVALID;
+  }
+  if (a->batch == 0) return EXENV_OK;
+  const size_t es = plan->desc.dtype == EXENV_F64 ? 8 : 4;
+  for (int d = 0; d < plan->dims.n_phys; ++d) {
+    if (!a->state_in[d] || !a->state_out[d]) {
+      set_error("exenv_step: state leaf %d is NULL", d);
+      return EXENV_ERR_NULL;
+    }
+    if (plan->desc.n_control > 0 && !a->ref[d]) {
+      set_error("exenv_step: control_state is set but reference leaf %d is NULL", d);
+      return EXENV_ERR_NULL;
+    }
+    if (!aligned_to(a->state_in[d], es) || !aligned_to(a->state_out[d], es)) {
+      set_error("exenv_step: state leaf %d is not aligned to its element size", d);
+      return EXENV_ERR_ALIGN;
+    }
+  }
+  if (!a->action || !a->obs) {
+    set_error("exenv_step: action/obs is NULL");
+    return EXENV_ERR_NULL;
+  }
+  if (!aligned_to(a->action, es) || !aligned_to(a->obs, es)) {
+    set_error("exenv_step: action/obs not aligned to the element size");
+    return EXENV_ERR_ALIGN;
+  }
+  return launch_step(*plan, *a, (cudaStream_t)stream);
+}
+
+int exenv_reset_pack(exenv_plan_t plan, const ExenvResetArgs *a, void *stream) {
+  if (!plan || !a) {
+    set_error("exenv_reset_pack: NULL plan/args");
+    return EXENV_ERR_NULL;
+  }
+  if (a->batch < 0 || a->mode < 0 || a->mode > 3) {
+    set_error("exenv_reset_pack: bad batch/mode");
+    return EXENV_ERR_INVALID;
+  }
+  if (a->batch == 0) return EXENV_OK;
+  for (int d = 0; d < plan->dims.n_phys; ++d)
+    if (!a->state_out[d]) {
+      set_error("exenv_reset_pack: state leaf %d is NULL", d);
+      return EXENV_ERR_NULL;
+    }
+  if (!a->obs || ((a->mode == EXENV_RESET_FROM_NORM || a->mode == EXENV_RESET_FROM_OBS) && !a->values)) {
+    set_error("exenv_reset_pack: obs/values is NULL");
+    return EXENV_ERR_NULL;
+  }
+  return launch_reset(*plan, *a, (cudaStream_t)stream);
+}
+
+int exenv_sim_ahead_shape(exenv_plan_t plan, int64_t n_actions, double obs_stepsize, double action_stepsize,
+                          int64_t *n_save, int64_t *n_steps) {
+  if (!plan) {
+    set_error("exenv_sim_ahead_shape: NULL plan");
+    return EXENV_ERR_NULL;
+  }
+  SimSchedule *s = nullptr;
+  const int E = 128;
+  int rc = get_schedule(plan, n_actions, obs_stepsize, action_stepsize, auto_tile_steps(*plan, E), false, &s);
+  if (rc != EXENV_OK) return rc;
+  if (n_save) *n_save = s->n_save;
+  if (n_steps) *n_steps = s->n_steps;
+  return EXENV_OK;
+}
+
+int exenv_schedule_build(const ExenvDesc *desc, int64_t n_actions, double obs_stepsize, double action_stepsize,
+                         int32_t tile_steps, ExenvScheduleInfo *info, uint64_t *words, double *dt, double *theta,
+                         int32_t *tiles) {
+  if (!desc || !info) {
+    set_error("exenv_schedule_build: NULL argument");
+    return EXENV_ERR_NULL;
+  }
+  ExenvPlan tmp;
+  tmp.desc = *desc;
+  tmp.deadtime = desc->env == EXENV_PMSM ? (int)desc->p[6] : 0;
+  SimSchedule s;
+  int rc = build_schedule(tmp, n_actions, obs_stepsize, action_stepsize, tile_steps > 0 ? tile_steps : 32, s);
+  if (rc != EXENV_OK) return rc;
+  info->n_save = s.n_save;
+  info->n_steps = s.n_steps;
+  info->n_tiles = s.n_tiles;
+  info->act_cap = s.act_cap;
+  info->save_cap = s.save_cap;
+  info->tile_steps = s.tile_steps;
+  if (words) memcpy(words, s.words.data(), s.words.size() * sizeof(uint64_t));
+  if (dt) memcpy(dt, s.dt.data(), s.dt.size() * sizeof(double));
+  if (theta) memcpy(theta, s.theta.data(), s.theta.size() * sizeof(double));
+  if (tiles) memcpy(tiles, s.tiles.data(), s.tiles.size() * sizeof(SimTile));
+  return EXENV_OK;
+}
+
+static int validate_sim(const ExenvPlan *plan, const ExenvSimArgs *a) {
+  if (!plan || !a) {
+    set_error("exenv_sim_ahead: NULL plan/args");
+    return EXENV_ERR_NULL;
+  }
+  if (a->batch < 0 || a->n_actions < 1) {
+    set_error("exenv_sim_ahead: bad batch / n_actions");
+    return EXENV_ERR_INVALID;
+  }
+  if (a->obs_stepsize > a->action_stepsize) {  // core_env.py:591-593
+    set_error("The action stepsize should be greater or equal to the observation stepsize.");
+    return EXENV_ERR_INVALID;
+  }
+  if (plan->desc.env == EXENV_PMSM && a->obs_stepsize != a->action_stepsize) {
+    set_error("PMSM sim_ahead requires obs_stepsize == action_stepsize (reference pmsm_env.py:787)");
+    return EXENV_ERR_UNSUPPORTED;
+  }
+  for (int d = 0; d < plan->dims.n_phys; ++d) {
+    if (!a->state_in[d]) {
+      set_error("exenv_sim_ahead: state leaf %d is NULL", d);
+      return EXENV_ERR_NULL;
+    }
+    if (plan->desc.n_control > 0 && !a->ref[d]) {
+      set_error("exenv_sim_ahead: control_state is set but reference leaf %d is NULL", d);
+      return EXENV_ERR_NULL;
+    }
+  }
+  if (!a->actions || !a->obs) {
+    set_error("exenv_sim_ahead: actions/obs is NULL");
+    return EXENV_ERR_NULL;
+  }
+  return EXENV_OK;
+}
+
+static int prepare_sim(ExenvPlan *plan, const ExenvSimArgs *a, int *E_out, SimSchedule **sch) {
+  const int E = sim_block_envs(a->batch, a->block_envs);
+  int K = a->tile_steps > 0 ? a->tile_steps : auto_tile_steps(*plan, E);
+  int rc = get_schedule(plan, a->n_actions, a->obs_stepsize, a->action_stepsize, K, true, sch);
+  if (rc != EXENV_OK) return rc;
+  const SimSchedule &s = **sch;
+  const int64_t max_steps = a->max_steps;
+  if (max_steps > 0 && s.n_steps > max_steps) {  // diffrax: RuntimeError from diffeqsolve(max_steps=4096)
+    set_error("The maximum number of solver steps was reached. Try increasing `max_steps`. (%lld > %lld)",
+              (long long)s.n_steps, (long long)max_steps);
+    return EXENV_ERR_MAX_STEPS;
+  }
+  const size_t smem = sim_smem_bytes(*plan, E, s.act_cap, s.save_cap);
+  if (smem > 227 * 1024) {
+    set_error("sim_ahead tile (%d steps x %d envs) needs %zu bytes of shared memory (> 227 KB)", K, E, smem);
+    return EXENV_ERR_INVALID;
+  }
+  *E_out = E;
+  return EXENV_OK;
+}
+
+int exenv_sim_ahead(exenv_plan_t plan, const ExenvSimArgs *a, void *stream) {
+  int rc = validate_sim(plan, a);
+  if (rc != EXENV_OK) return rc;
+  if (a->batch == 0) return EXENV_OK;
+  int E = 0;
+  SimSchedule *sch = nullptr;
+  rc = prepare_sim(plan, a, &E, &sch);
+  if (rc != EXENV_OK) return rc;
+  ExenvSimArgs b = *a;
+  b.block_envs = E;
+  return launch_sim(*plan, b, *sch, (cudaStream_t)stream);
+}
+
+// Host-buffer variant: what a caller holding CPU arrays (the reference's CPU-JAX user) pays end to end.  The batch is
+// cut into chunks; each chunk's inputs go host->device, the persistent kernel runs, outputs come back device->host, on
+// NSTREAM streams so copies in both directions overlap the kernel.
+int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *h, int64_t chunk_envs) {
+  int rc = validate_sim(plan, h);
+  if (rc != EXENV_OK) return rc;
+  if (h->batch == 0) return EXENV_OK;
+  EX_CUDA(cudaSetDevice(plan->device));
+  const size_t es = plan->desc.dtype == EXENV_F64 ? 8 : 4;
+  const int D = plan->dims.n_phys, A = plan->dims.n_act, NODE = plan->dims.n_ode;
+  const int OW = plan->dims.n_obs + plan->desc.n_control, nt = plan->dims.n_trunc;
+  int64_t n_save = 0, n_steps = 0;
+  rc = exenv_sim_ahead_shape(plan, h->n_actions, h->obs_stepsize, h->action_stepsize, &n_save, &n_steps);
+  if (rc != EXENV_OK) return rc;
+  const int64_t T = h->n_actions;
+  // bytes per environment on the device
+  size_t per_env = es * ((size_t)D + (size_t)T * A + (size_t)n_save * OW);
+  for (int d = 0; d < D; ++d) {
+    if (h->traj[d]) per_env += es * (size_t)n_save;
+    if (h->last[d]) per_env += es;
+    if (h->ref[d]) per_env += es;
+  }
+  for (int d = 0; d < NODE; ++d)
+    if (h->k_last[d]) per_env += es;
+  if (h->reward) per_env += es * (size_t)(n_save - 1);
+  if (h->truncated) per_env += (size_t)n_save * nt;
+  if (h->terminated) per_env += (size_t)(n_save - 1);
+  constexpr int NSTREAM = 3;
+  if (chunk_envs <= 0) {
+    const size_t target = (size_t)768 << 20;  // ~0.75 GiB of device workspace per pipeline stage
+    chunk_envs = (int64_t)std::max<size_t>(128, (target / per_env) / 128 * 128);
+  }
+  chunk_envs = std::min<int64_t>(chunk_envs, h->batch);
+  const size_t ws_bytes = per_env * (size_t)chunk_envs + (64 << 10);
+  void *ws[NSTREAM] = {nullptr, nullptr, nullptr};
+  cudaStream_t st[NSTREAM];
+  int n_st = (int)std::min<int64_t>(NSTREAM, (h->batch + chunk_envs - 1) / chunk_envs);
+  for (int i = 0; i < n_st; ++i) {
+    EX_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    EX_CUDA(cudaMalloc(&ws[i], ws_bytes));
+  }
+  int result = EXENV_OK;
+  int slot = 0;
+  for (int64_t b0 = 0; b0 < h->batch && result == EXENV_OK; b0 += chunk_envs, slot = (slot + 1) % n_st) {
+    const int64_t nb = std::min<int64_t>(chunk_envs, h->batch - b0);
+    cudaStream_t s = st[slot];
+    char *cur = (char *)ws[slot];
+    auto take = [&](size_t bytes) {
+      char *p = cur;
+      cur += (bytes + 255) & ~(size_t)255;
+      return (void *)p;
+    };
+    ExenvSimArgs d = *h;
+    d.batch = nb;
+    struct Back {
+      void *host;
+      void *dev;
+      size_t bytes;
+    };
+    std::vector<Back> back;
+    auto in = [&](const void *host, size_t per, size_t off_elems) -> const void * {
+      void *dv = take(per * nb);
+      cudaMemcpyAsync(dv, (const char *)host + off_elems, per * nb, cudaMemcpyHostToDevice, s);
+      return dv;
+    };
+    auto outb = [&](void *host, size_t per) -> void * {
+      void *dv = take(per * nb);
+      back.push_back({(char *)host + per * b0, dv, per * (size_t)nb});
+      return dv;
+    };
+    for (int i = 0; i < D; ++i) {
+      d.state_in[i] = in(h->state_in[i], es, es * b0);
+      if (h->ref[i]) d.ref[i] = in(h->ref[i], es, es * b0);
+      if (h->traj[i]) d.traj[i] = outb(h->traj[i], es * (size_t)n_save);
+      if (h->last[i]) d.last[i] = outb(h->last[i], es);
+    }
+    for (int i = 0; i < NODE; ++i)
+      if (h->k_last[i]) d.k_last[i] = outb(h->k_last[i], es);
+    d.actions = in(h->actions, es * (size_t)T * A, es * (size_t)T * A * b0);
+    d.obs = outb(h->obs, es * (size_t)n_save * OW);
+    if (h->reward) d.reward = outb(h->reward, es * (size_t)(n_save - 1));
+    if (h->truncated) d.truncated = (uint8_t *)outb(h->truncated, (size_t)n_save * nt);
+    if (h->terminated) d.terminated = (uint8_t *)outb(h->terminated, (size_t)(n_save - 1));
+    result = exenv_sim_ahead(plan, &d, s);
+    if (result != EXENV_OK) break;
+    for (const Back &bk : back) cudaMemcpyAsync(bk.host, bk.dev, bk.bytes, cudaMemcpyDeviceToHost, s);
+  }
+  for (int i = 0; i < n_st; ++i) {
+    cudaError_t e = cudaStreamSynchronize(st[i]);
+    if (e != cudaSuccess && result == EXENV_OK) {
+      set_error("exenv_sim_ahead_host: %s", cudaGetErrorString(e));
+      result = EXENV_ERR_CUDA;
+    }
+    cudaFree(ws[i]);
+    cudaStreamDestroy(st[i]);
+  }
+  return result;
+}
+
+}  // extern "C"

@@ -1,0 +1,434 @@
+// exenv_envs.cuh -- per-environment physics: ODE right-hand sides, post-step wrap/clip, observation, reward,
+// truncated/terminated, PMSM inverter voltage limit and flux-map look-up.  Pure scalar code (no memory layout
+// knowledge): the kernels in exenv_step.cu / exenv_sim.cu own the data movement.
+//
+// Parameter vector `p` (same slots as ExenvDesc.p, include/exenv_b200.h):
+//   [static params..., (min,max) per PhysicalState field..., (min,max) per Action field...]
+// Reference citations are relative to /root/reference/exciting_environments/.
+#pragma once
+
+#include "exenv_math.cuh"
+
+namespace exenv {
+
+// ---- PMSM flux maps ----------------------------------------------------------------------------------------
+// Device layout prepared at plan creation: grids gx[nx] (i_d), gy[ny] (i_q) and cells[(ix*ny + iy)*6 + q] with
+// q = L_dd, L_dq, L_qd, L_qq, Psi_d, Psi_q -- the six RegularGridInterpolator objects of pmsm_env.py:352-361 share
+// one index/weight computation here.
+template <typename T>
+struct LutView {
+  const T *gx;
+  const T *gy;
+  const T *cells;
+  int nx, ny;
+  T inv_dx, inv_dy;  // 1 / grid spacing: only used for the initial cell guess
+};
+
+// searchsorted(g, x, side="left") - 1 clipped to [0, n-2]  (jax RegularGridInterpolator._find_indices)
+template <typename T>
+EX_HD int lut_cell(const T *g, int n, T inv_d, T x) {
+  T gf = (x - g[0]) * inv_d;
+  int i = (gf > (T)0) ? ((gf < (T)(n - 2)) ? (int)gf : n - 2) : 0;
+  while (i > 0 && !(g[i] < x)) --i;
+  while (i < n - 2 && g[i + 1] < x) ++i;
+  return i;
+}
+
+template <typename T, int FIRST, int COUNT>
+EX_HD void lut_eval(const LutView<T> &L, T id, T iq, T *out) {
+  const int i = lut_cell<T>(L.gx, L.nx, L.inv_dx, id);
+  const int j = lut_cell<T>(L.gy, L.ny, L.inv_dy, iq);
+  const T yi = (id - L.gx[i]) / (L.gx[i + 1] - L.gx[i]);
+  const T yj = (iq - L.gy[j]) / (L.gy[j + 1] - L.gy[j]);
+  const T w00 = ((T)1 - yi) * ((T)1 - yj);
+  const T w01 = ((T)1 - yi) * yj;
+  const T w10 = yi * ((T)1 - yj);
+  const T w11 = yi * yj;
+  const T *c00 = L.cells + ((long)i * L.ny + j) * 6;
+  const T *c10 = c00 + (long)L.ny * 6;
+#pragma unroll
+  for (int q = 0; q < COUNT; ++q) {
+    T v = c00[FIRST + q] * w00;
+    v += c00[6 + FIRST + q] * w01;
+    v += c10[FIRST + q] * w10;
+    v += c10[6 + FIRST + q] * w11;
+    out[q] = v;
+  }
+}
+
+struct NoAux {};
+
+template <typename T>
+struct PmsmAux {
+  T omega_el;  // constant over a step / a sim_ahead call (pmsm_env.py:546, 639)
+  LutView<T> lut;
+};
+
+// ---- Pendulum (pendulum/pendulum_env.py) -------------------------------------------------------------------
+template <typename T>
+struct Pendulum {
+  static constexpr int ID = 0, D = 2, NODE = 2, A = 1, O = 2, NSTATIC = 3, NTRUNC_BASE = 2;
+  static constexpr bool IS_PMSM = false, SATURATED = false;
+  using Aux = NoAux;
+  // :144-150  p = g, l, m
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+    const T g = p[0], l = p[1], m = p[2];
+    dy[0] = y[1];
+    dy[1] = (u[0] + l * m * g * Mth<T>::sin(y[0])) / (m * (l * l));
+  }
+  EX_HD static void post(T *y) { y[0] = wrap_pi<T>(y[0]); }  // :188, :241
+  EX_HD static bool is_angle(int f) { return f == 0; }
+  EX_HD static void default_norm_state(T *z) {  // :265-268
+    z[0] = (T)1;
+    z[1] = (T)0;
+  }
+};
+
+// ---- Mass-spring-damper (mass_spring_damper/mass_spring_damper_env.py) --------------------------------------
+template <typename T>
+struct MassSpringDamper {
+  static constexpr int ID = 1, D = 2, NODE = 2, A = 1, O = 2, NSTATIC = 3, NTRUNC_BASE = 2;
+  static constexpr bool IS_PMSM = false, SATURATED = false;
+  using Aux = NoAux;
+  // :142-148  p = d, k, m
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+    const T d = p[0], k = p[1], m = p[2];
+    dy[0] = y[1];
+    dy[1] = (u[0] - d * y[1] - k * y[0]) / m;
+  }
+  EX_HD static void post(T *) {}
+  EX_HD static bool is_angle(int) { return false; }
+  EX_HD static void default_norm_state(T *z) { z[0] = z[1] = (T)0; }  // :261-265
+};
+
+// ---- Fluid tank (fluid_tank/fluid_tank_env.py) ---------------------------------------------------------------
+template <typename T>
+struct FluidTank {
+  static constexpr int ID = 2, D = 1, NODE = 1, A = 1, O = 1, NSTATIC = 4, NTRUNC_BASE = 1;
+  static constexpr bool IS_PMSM = false, SATURATED = false;
+  using Aux = NoAux;
+  // :97-106  p = base_area, orifice_area, c_d, g
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+    const T Ab = p[0], Ao = p[1], cd = p[2], g = p[3];
+    const T h = y[0] < (T)0 ? (T)0 : y[0];
+    dy[0] = u[0] / Ab - cd * Ao / Ab * Mth<T>::sqrt((T)2 * g * h);
+  }
+  EX_HD static void post(T *y) { y[0] = y[0] < (T)0 ? (T)0 : y[0]; }  // :146, :196
+  EX_HD static bool is_angle(int) { return false; }
+  EX_HD static void default_norm_state(T *z) { z[0] = (T)0; }  // :221-224
+};
+
+// ---- Cart-pole (cart_pole/cart_pole_env.py) ------------------------------------------------------------------
+template <typename T>
+struct CartPole {
+  static constexpr int ID = 3, D = 4, NODE = 4, A = 1, O = 4, NSTATIC = 6, NTRUNC_BASE = 4;
+  static constexpr bool IS_PMSM = false, SATURATED = false;
+  using Aux = NoAux;
+  // :159-180  p = mu_p, mu_c, l, m_p, m_c, g ; y = deflection, velocity, theta, omega
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+    const T mu_p = p[0], mu_c = p[1], l = p[2], m_p = p[3], m_c = p[4], g = p[5];
+    const T v = y[1], th = y[2], om = y[3];
+    T s, c;
+    Mth<T>::sincos(th, &s, &c);
+    const T sg = sign_of<T>(v);
+    const T d_om = (g * s + c * ((-u[0] - m_p * l * (om * om) * s + mu_c * sg) / (m_c + m_p)) - (mu_p * om) / (m_p * l)) /
+                   (l * ((T)(4.0 / 3.0) - (m_p * (c * c)) / (m_c + m_p)));
+    const T d_v = (u[0] + m_p * l * ((om * om) * s - d_om * c) - mu_c * sg) / (m_c + m_p);
+    dy[0] = v;
+    dy[1] = d_v;
+    dy[2] = om;
+    dy[3] = d_om;
+  }
+  EX_HD static void post(T *y) { y[2] = wrap_pi<T>(y[2]); }  // :229
+  EX_HD static bool is_angle(int f) { return f == 2; }
+  EX_HD static void default_norm_state(T *z) {  // :317-322
+    z[0] = z[1] = z[3] = (T)0;
+    z[2] = (T)1;
+  }
+};
+
+// ---- Acrobot (acrobot/acrobot_env.py) ------------------------------------------------------------------------
+template <typename T>
+struct Acrobot {
+  static constexpr int ID = 4, D = 4, NODE = 4, A = 1, O = 4, NSTATIC = 9, NTRUNC_BASE = 4;
+  static constexpr bool IS_PMSM = false, SATURATED = false;
+  using Aux = NoAux;
+  // :171-197  p = g, l_1, l_2, m_1, m_2, l_c1, l_c2, I_1, I_2 ; y = theta_1, theta_2, omega_1, omega_2
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+    const T g = p[0], l1 = p[1], m1 = p[3], m2 = p[4], lc1 = p[5], lc2 = p[6], I1 = p[7], I2 = p[8];
+    const T th1 = y[0], th2 = y[1], om1 = y[2], om2 = y[3];
+    T s2, c2;
+    Mth<T>::sincos(th2, &s2, &c2);
+    const T d11 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2 + (T)2 * l1 * lc2 * c2) + I1 + I2;
+    const T d12 = m2 * (lc2 * lc2 + l1 * lc2 * c2) + I2;
+    const T d22 = m2 * (lc2 * lc2) + I2;
+    const T h1 = -m2 * l1 * lc2 * s2 * (om2 * om2) - (T)2 * m2 * l1 * lc2 * s2 * om1 * om2;
+    const T h2 = m2 * l1 * lc2 * s2 * (om1 * om1);
+    const T ca = Mth<T>::cos(th1 + Cst<T>::half_pi());
+    const T cb = Mth<T>::cos(th1 + th2 + Cst<T>::half_pi());
+    const T phi1 = (m1 * lc1 + m2 * l1) * g * ca + m2 * lc2 * g * cb;
+    const T phi2 = m2 * lc2 * g * cb;
+    const T d_om1 = (T)1 / (d12 - d22 / d12 * d11) * (u[0] + d22 / d12 * (h1 + phi1) - h2 - phi2);
+    const T d_om2 = (-d11 * d_om1 - h1 - phi1) / d12;
+    dy[0] = om1;
+    dy[1] = om2;
+    dy[2] = d_om1;
+    dy[3] = d_om2;
+  }
+  EX_HD static void post(T *y) {  // :247-248
+    y[0] = wrap_pi<T>(y[0]);
+    y[1] = wrap_pi<T>(y[1]);
+  }
+  EX_HD static bool is_angle(int f) { return f == 0 || f == 1; }
+  EX_HD static void default_norm_state(T *z) {  // :338-343
+    z[0] = (T)1;
+    z[1] = z[2] = z[3] = (T)0;
+  }
+};
+
+// ---- PMSM (pmsm/pmsm_env.py) -----------------------------------------------------------------------------------
+// PhysicalState fields: 0 u_d_buffer, 1 u_q_buffer, 2 epsilon, 3 i_d, 4 i_q, 5 torque, 6 omega_el (:281-291)
+// ODE state y = (i_d, i_q, epsilon) (:555).  p = p, r_s, l_d, l_q, psi_p, u_dc, deadtime.
+template <typename T, bool SAT>
+struct Pmsm {
+  static constexpr int ID = 5, D = 7, NODE = 3, A = 2, O = 8, NSTATIC = 7, NTRUNC_BASE = 1;
+  static constexpr bool IS_PMSM = true;
+  static constexpr bool SATURATED = SAT;
+  using Aux = PmsmAux<T>;
+
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &aux, T *dy) {
+    const T r_s = p[1];
+    const T id = y[0], iq = y[1], w = aux.omega_el;
+    if constexpr (!SAT) {  // :509-523 linear_ode
+      const T l_d = p[2], l_q = p[3], psi_p = p[4];
+      dy[0] = (u[0] + w * l_q * iq - r_s * id) / l_d;
+      dy[1] = (u[1] - w * (l_d * id + psi_p) - r_s * iq) / l_q;
+    } else {  // :487-507 nonlinear_ode
+      T q[6];
+      lut_eval<T, 0, 6>(aux.lut, id, iq, q);
+      // jnp.linalg.inv of the 2x2 differential-inductance matrix: LU with partial pivoting + two solves
+      const bool swap = Mth<T>::abs(q[2]) > Mth<T>::abs(q[0]);
+      const T b00 = swap ? q[2] : q[0], b01 = swap ? q[3] : q[1];
+      const T b10 = swap ? q[0] : q[2], b11 = swap ? q[1] : q[3];
+      const T lf = b10 / b00;
+      const T u11 = b11 - lf * b01;
+      T inv[2][2];
+#pragma unroll
+      for (int col = 0; col < 2; ++col) {
+        const T e0 = (T)((swap ? 1 : 0) == col), e1 = (T)((swap ? 0 : 1) == col);
+        const T y0 = e0, y1 = e1 - lf * y0;
+        const T x1 = y1 / u11;
+        const T x0 = (y0 - b01 * x1) / b00;
+        inv[0][col] = x0;
+        inv[1][col] = x1;
+      }
+      const T jp0 = -q[5], jp1 = q[4];  // J_k @ (Psi_d, Psi_q)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const T d1 = (-inv[r][0] * r_s) * id + (-inv[r][1] * r_s) * iq;
+        const T d2 = inv[r][0] * u[0] + inv[r][1] * u[1];
+        const T d3 = ((-inv[r][0]) * jp0 + (-inv[r][1]) * jp1) * w;
+        dy[r] = d1 + d2 + d3;
+      }
+    }
+    dy[2] = w;
+  }
+  EX_HD static void post(T *y) { y[2] = wrap_pi<T>(y[2]); }  // :571, :669
+  EX_HD static bool is_angle(int) { return false; }
+
+  // :365-381 currents_to_torque / currents_to_torque_saturated
+  EX_HD static T torque(T id, T iq, const T *p, const Aux &aux) {
+    if constexpr (!SAT) {
+      return (T)1.5 * p[0] * (p[4] + (p[2] - p[3]) * id) * iq;
+    } else {
+      T q[2];
+      lut_eval<T, 4, 2>(aux.lut, id, iq, q);
+      return (T)1.5 * p[0] * (q[0] * iq - q[1] * id);
+    }
+  }
+};
+
+// :594-616 constraint_denormalization, :82-89 step_eps, :46-72 dq<->alpha/beta, :92-102 apply_hex_constraint.
+// ROTATION_MAP is complex64 (:37-43): the rotation constants are float32-rounded in both precisions.
+// adv = (deadtime + 0.5) * tau (Python-double product, host side).  a_min/a_max: action normalisation slots.
+template <typename T>
+EX_HD void pmsm_clip(T a0, T a1, T eps, T omega_el, T u_dc, T adv, const T *an, T *ud_out, T *uq_out) {
+  T ud = denorm_mm<T>(a0, an[0], an[1]);
+  T uq = denorm_mm<T>(a1, an[2], an[3]);
+  const T half_dc = u_dc / (T)2;
+  const T sc = (T)1 / half_dc;
+  ud = ud * sc;
+  uq = uq * sc;
+  T ea = eps + adv * omega_el;
+  ea = pymod<T>(ea, Cst<T>::two_pi());
+  if (ea > Cst<T>::pi()) ea = ea + (T)-2 * Cst<T>::pi();
+  T sm, cm;
+  Mth<T>::sincos(-ea, &sm, &cm);
+  const T ua = cm * ud + sm * uq;
+  const T ub = -sm * ud + cm * uq;
+  const T ang = Mth<T>::atan2(ub, ua);
+  const T third = (T)(2.0 / 3.0 * 3.141592653589793);
+  const int i0 = Mth<T>::sin(ang - third * (T)0) >= (T)0;
+  const int i1 = Mth<T>::sin(ang - third * (T)1) >= (T)0;
+  const int i2 = Mth<T>::sin(ang - third * (T)2) >= (T)0;
+  const T H = (T)0.5f, S3 = (T)0.8660254037844386f;
+  T rr = (T)1, ri = (T)0;
+  const int code = (i0 << 2) | (i1 << 1) | i2;
+  if (code == 5) { rr = H; ri = S3; }
+  else if (code == 6) { rr = H; ri = -S3; }
+  else if (code == 2) { rr = -H; ri = -S3; }
+  else if (code == 3) { rr = (T)-1; ri = (T)0; }
+  else if (code == 1) { rr = -H; ri = S3; }
+  T zr = ua * rr - ub * ri, zi = ua * ri + ub * rr;
+  const T lim_r = (T)(2.0 / 3.0);
+  const T lim_i = (T)(2.0 / 3.0) * Mth<T>::sqrt((T)3);
+  zr = zr < -lim_r ? -lim_r : (zr > lim_r ? lim_r : zr);
+  zi = zi < (T)0 ? (T)0 : (zi > lim_i ? lim_i : zi);
+  const T wr = zr * rr - zi * (-ri), wi = zr * (-ri) + zi * rr;
+  T sp, cp;
+  Mth<T>::sincos(ea, &sp, &cp);
+  const T vd = cp * wr + sp * wi;
+  const T vq = -sp * wr + cp * wi;
+  *ud_out = vd * half_dc;
+  *uq_out = vq * half_dc;
+}
+
+// ---- observation / reward / flags ------------------------------------------------------------------------------
+// Base observation (without reference entries): e.g. pendulum_env.py:311-329; PMSM pmsm_env.py:898-919 (order
+// i_d, i_q, omega_el, torque, cos eps, sin eps, u_d_buffer, u_q_buffer -- not the order of `_obs_description`).
+template <class Env, typename T>
+EX_HD T obs_entry(int o, const T *s, const T *p) {
+  const T *pn = p + Env::NSTATIC;
+  if constexpr (Env::IS_PMSM) {
+    switch (o) {
+      case 0: return norm_mm<T>(s[3], pn[6], pn[7]);
+      case 1: return norm_mm<T>(s[4], pn[8], pn[9]);
+      case 2: return norm_mm<T>(s[6], pn[12], pn[13]);
+      case 3: return norm_mm<T>(s[5], pn[10], pn[11]);
+      case 4: return Mth<T>::cos(s[2]);
+      case 5: return Mth<T>::sin(s[2]);
+      case 6: return norm_mm<T>(s[0], pn[0], pn[1]);
+      default: return norm_mm<T>(s[1], pn[2], pn[3]);
+    }
+  } else {
+    T v = s[0], mn = pn[0], mx = pn[1];
+#pragma unroll
+    for (int i = 1; i < Env::D; ++i)
+      if (o == i) {
+        v = s[i];
+        mn = pn[2 * i];
+        mx = pn[2 * i + 1];
+      }
+    return norm_mm<T>(v, mn, mx);
+  }
+}
+
+template <class Env, typename T>
+EX_HD void observe(const T *s, const T *p, T *obs) {
+#pragma unroll
+  for (int o = 0; o < Env::O; ++o) obs[o] = obs_entry<Env, T>(o, s, p);
+}
+
+// Normalised field `f` of a physical-state-shaped vector (state or reference).
+template <class Env, typename T>
+EX_HD T norm_field(int f, const T *s, const T *p) {
+  const T *pn = p + Env::NSTATIC;
+  T v = s[0], mn = pn[0], mx = pn[1];
+#pragma unroll
+  for (int i = 1; i < Env::D; ++i)
+    if (f == i) {
+      v = s[i];
+      mn = pn[2 * i];
+      mx = pn[2 * i + 1];
+    }
+  return norm_mm<T>(v, mn, mx);
+}
+template <class Env, typename T>
+EX_HD T field_of(int f, const T *s) {
+  T v = s[0];
+#pragma unroll
+  for (int i = 1; i < Env::D; ++i)
+    if (f == i) v = s[i];
+  return v;
+}
+
+// pmsm_env.py:1014-1037 torque_reward_func (i_lim_multiplier = 1, gamma = 0.85), on normalised quantities
+template <typename T>
+EX_HD T pmsm_torque_reward(T i_d, T i_q, T tq, T tq_ref) {
+  const T i_s = Mth<T>::sqrt(i_d * i_d + i_q * i_q);
+  const T i_n = (T)1 / (T)1;
+  const T i_d_plus = (T)0.2 * i_n;
+  const T tol = (T)0.01;
+  T rew = (T)0;
+  if (i_s > (T)1) rew = (T)-1 * Mth<T>::abs(i_s);
+  if (i_s < (T)1.0 && i_s > i_n) rew = (T)0.5 * ((T)1 - (i_s - i_n) / ((T)1 - i_n)) - (T)1;
+  if (i_s < i_n && i_d > i_d_plus) rew = (T)-0.5 * ((i_d - i_d_plus) / (i_n - i_d_plus));
+  if (i_s < i_n && i_d < i_d_plus && Mth<T>::abs(tq - tq_ref) > tol)
+    rew = (T)0.5 * ((T)1 - Mth<T>::abs((tq_ref - tq) / (T)2));
+  if (i_s < i_n && i_d < i_d_plus && Mth<T>::abs(tq - tq_ref) < tol) rew = (T)1 - (T)0.5 * i_s;
+  return rew * ((T)1 - (T)0.85);
+}
+
+// generate_reward (pendulum_env.py:297-309, mass_spring_damper_env.py:295-302, fluid_tank_env.py:252-259,
+// cart_pole_env.py:354-366, acrobot_env.py:375-388, pmsm_env.py:985-1008).  control_state = [] -> 0.
+template <class Env, typename T>
+EX_HD T reward_of(const T *s, const T *ref, const T *p, int n_control, const int *control) {
+  T rew = (T)0;
+  if constexpr (Env::IS_PMSM) {
+    bool has_id = false, has_iq = false, has_tq = false;
+    for (int j = 0; j < n_control; ++j) {
+      has_id |= control[j] == 3;
+      has_iq |= control[j] == 4;
+      has_tq |= control[j] == 5;
+    }
+    const T idn = norm_field<Env, T>(3, s, p), iqn = norm_field<Env, T>(4, s, p);
+    if (has_id && has_iq) {
+      const T idr = norm_field<Env, T>(3, ref, p), iqr = norm_field<Env, T>(4, ref, p);
+      const T mse = (T)0.5 * ((idn - idr) * (idn - idr)) + (T)0.5 * ((iqn - iqr) * (iqn - iqr));
+      rew += (T)-1 * (mse * ((T)1 - (T)0.85));
+    }
+    if (has_tq) rew += pmsm_torque_reward<T>(idn, iqn, norm_field<Env, T>(5, s, p), norm_field<Env, T>(5, ref, p));
+  } else {
+    for (int j = 0; j < n_control; ++j) {
+      const int f = control[j];
+      if (Env::is_angle(f)) {
+        const T th = field_of<Env, T>(f, s), thr = field_of<Env, T>(f, ref);
+        const T a = Mth<T>::sin(th) - Mth<T>::sin(thr);
+        const T b = Mth<T>::cos(th) - Mth<T>::cos(thr);
+        rew += -(a * a + b * b);
+      } else {
+        const T e = norm_field<Env, T>(f, s, p) - norm_field<Env, T>(f, ref, p);
+        rew += -(e * e);
+      }
+    }
+  }
+  return rew;
+}
+
+// generate_truncated: |obs| > 1 over the whole observation incl. reference entries (pendulum_env.py:381-385);
+// fluid tank: constant [0] (fluid_tank_env.py:323-326); PMSM: [sqrt(i_d_n^2 + i_q_n^2) > 1] (pmsm_env.py:972-979).
+template <class Env>
+EX_HD constexpr int trunc_dim(int n_control) {
+  return (Env::ID == 2 || Env::ID == 5) ? 1 : Env::O + n_control;
+}
+template <class Env, typename T>
+EX_HD bool trunc_entry(int i, const T *s, const T *obs_full, const T *p) {
+  if constexpr (Env::ID == 2) {
+    return false;
+  } else if constexpr (Env::IS_PMSM) {
+    const T idn = norm_field<Env, T>(3, s, p), iqn = norm_field<Env, T>(4, s, p);
+    return Mth<T>::sqrt(idn * idn + iqn * iqn) > (T)1;
+  } else {
+    return Mth<T>::abs(obs_full[i]) > (T)1;
+  }
+}
+// generate_terminated: reward == 0 (pendulum_env.py:387-390); tank False (fluid_tank_env.py:328-331);
+// PMSM = truncated (pmsm_env.py:981-983)
+template <class Env, typename T>
+EX_HD bool terminated_of(T reward, bool trunc0) {
+  if constexpr (Env::ID == 2) return false;
+  if constexpr (Env::IS_PMSM) return trunc0;
+  return reward == (T)0;
+}
+
+}  // namespace exenv

@@ -1,0 +1,76 @@
+// exenv_internal.h -- host-side structures shared by the C-ABI translation unit (exenv_api.cu) and the kernel
+// launchers (exenv_step.cu, exenv_sim.cu).  Not part of the public ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/exenv_b200.h"
+
+namespace exenv {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+// One tile of the persistent sim_ahead kernel: a run of solver steps whose ZOH actions and saved samples are
+// staged in shared memory together.
+struct SimTile {
+  int step_begin, step_count;
+  int act_lo, act_cnt;    // staged action-index range (indices into the ZOH'ed sequence)
+  int save_begin, save_cnt;
+};
+
+// Environment-independent emulation of diffrax.diffeqsolve's constant-step loop in the plan dtype:
+// per solver step the step length, the ZOH action index of every stage and the saves that fall into it.
+struct SimSchedule {
+  int64_t n_actions = 0, n_save = 0, n_steps = 0;
+  int tile_steps = 0, n_tiles = 0, act_cap = 0, save_cap = 0;
+  // device copies
+  uint64_t *d_words = nullptr;  // bits 0-31 min action index, 32-45 seven 2-bit stage deltas, 46-49 #saves
+  void *d_dt = nullptr;         // T[n_steps]   tnext - tprev
+  void *d_theta = nullptr;      // T[n_save]    dense-output abscissa of every save, in save order
+  SimTile *d_tiles = nullptr;
+  // host copies (tests / shape queries)
+  std::vector<uint64_t> words;
+  std::vector<double> dt, theta;
+  std::vector<SimTile> tiles;
+};
+
+struct DevLut {
+  void *blob = nullptr;  // [gx | gy | cells] in the plan dtype, 16-byte padded sections
+  size_t bytes = 0, off_gy = 0, off_cells = 0;
+  int nx = 0, ny = 0;
+  double inv_dx = 0, inv_dy = 0;
+};
+
+}  // namespace exenv
+
+struct ExenvPlan {
+  ExenvDesc desc;
+  ExenvDims dims;
+  int device = 0;
+  int deadtime = 0;        // PMSM static_params.deadtime
+  double pmsm_adv = 0;     // (deadtime + 0.5) * tau
+  bool per_env = false;    // any pp[i] != NULL
+  exenv::DevLut lut;
+  std::mutex mu;
+  std::map<std::tuple<int64_t, double, double, int>, exenv::SimSchedule> schedules;
+};
+
+namespace exenv {
+
+int launch_step(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
+int launch_reset(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream);
+int launch_sim(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
+// Shared-memory bytes the sim kernel needs for (block_envs, act_cap, save_cap); used to size tiles.
+int sim_block_envs(int64_t batch, int requested);
+size_t sim_smem_bytes(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap);
+
+}  // namespace exenv

@@ -1,0 +1,171 @@
+// exenv_math.cuh -- scalar building blocks shared by all kernels (device) and by the test-only host harness.
+// Nothing here touches memory; every function is a pure scalar transform so that the same source is
+// compiled by nvcc for sm_100a (product) and by g++ for tests/hostcheck (device-math host harness).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define EX_HD __host__ __device__ __forceinline__
+#else
+#define EX_HD inline
+#endif
+
+namespace exenv {
+
+// ---- dtype-dispatched libm -----------------------------------------------------------------------------------
+template <typename T>
+struct Mth;
+
+template <>
+struct Mth<float> {
+  static EX_HD float sin(float x) { return ::sinf(x); }
+  static EX_HD float cos(float x) { return ::cosf(x); }
+  static EX_HD void sincos(float x, float *s, float *c) {
+#if defined(__CUDA_ARCH__)
+    ::sincosf(x, s, c);
+#else
+    *s = ::sinf(x);
+    *c = ::cosf(x);
+#endif
+  }
+  static EX_HD float sqrt(float x) { return ::sqrtf(x); }
+  static EX_HD float fmod(float x, float y) { return ::fmodf(x, y); }
+  static EX_HD float atan2(float y, float x) { return ::atan2f(y, x); }
+  static EX_HD float abs(float x) { return ::fabsf(x); }
+};
+
+template <>
+struct Mth<double> {
+  static EX_HD double sin(double x) { return ::sin(x); }
+  static EX_HD double cos(double x) { return ::cos(x); }
+  static EX_HD void sincos(double x, double *s, double *c) {
+#if defined(__CUDA_ARCH__)
+    ::sincos(x, s, c);
+#else
+    *s = ::sin(x);
+    *c = ::cos(x);
+#endif
+  }
+  static EX_HD double sqrt(double x) { return ::sqrt(x); }
+  static EX_HD double fmod(double x, double y) { return ::fmod(x, y); }
+  static EX_HD double atan2(double y, double x) { return ::atan2(y, x); }
+  static EX_HD double abs(double x) { return ::fabs(x); }
+};
+
+template <typename T>
+EX_HD T nan_of() {
+  return (T)NAN;
+}
+
+// MinMaxNormalization (reference utils.py:13-17).  True divisions are kept: norm(denorm(z)) == z exactly at the
+// default resets only holds with IEEE division.
+template <typename T>
+EX_HD T norm_mm(T x, T mn, T mx) {
+  return (T)2 * (x - mn) / (mx - mn) - (T)1;
+}
+template <typename T>
+EX_HD T denorm_mm(T z, T mn, T mx) {
+  return (z + (T)1) / (T)2 * (mx - mn) + mn;
+}
+
+// jnp `%`: C fmod followed by the sign correction (jax.numpy.remainder); SURVEY Appendix A.
+template <typename T>
+EX_HD T pymod(T x, T y) {
+  T r = Mth<T>::fmod(x, y);
+  if (r != (T)0 && ((r < (T)0) != (y < (T)0))) r += y;
+  return r;
+}
+
+template <typename T>
+struct Cst {
+  static constexpr double PI_D = 3.141592653589793;
+  static EX_HD T pi() { return (T)PI_D; }
+  static EX_HD T two_pi() { return (T)(2 * PI_D); }
+  static EX_HD T half_pi() { return (T)(PI_D / 2); }
+};
+
+// theta <- ((theta + pi) % (2 pi)) - pi   (pendulum_env.py:188, cart_pole_env.py:229, acrobot_env.py:247-248,
+// pmsm_env.py:571)
+template <typename T>
+EX_HD T wrap_pi(T th) {
+  return pymod<T>(th + Cst<T>::pi(), Cst<T>::two_pi()) - Cst<T>::pi();
+}
+
+template <typename T>
+EX_HD T sign_of(T v) {
+  return (T)((v > (T)0) - (v < (T)0));
+}
+
+// ---- Tsit5 (diffrax.Tsit5; Tsitouras 2011).  SURVEY Appendix B.2 --------------------------------------------
+// Stage increments are k_i = f_i * dt (diffrax "vf_prod"); stage states y0 + sum_j a_ij k_j; the solution is the
+// stage-7 state (FSAL/SSAL tableau).  `rhs(stage, y, f)` evaluates the vector field for stage index 1..6
+// (0-based; stage 0's derivative f0 is supplied by the caller: FSAL carry or a fresh evaluation).
+// k[0..6][N] are returned for dense output; f_last = f(t0 + dt, y1).
+template <typename T, int N, class F>
+EX_HD void tsit5_step(const T *y0, const T *f0, T dt, F &&rhs, T *y1, T *f_last, T (*k)[N]) {
+  constexpr T a21 = (T)0.161;
+  constexpr T a31 = (T)-0.008480655492356989, a32 = (T)0.335480655492357;
+  constexpr T a41 = (T)2.8971530571054935, a42 = (T)-6.359448489975075, a43 = (T)4.3622954328695815;
+  constexpr T a51 = (T)5.325864828439257, a52 = (T)-11.748883564062828, a53 = (T)7.4955393428898365,
+              a54 = (T)-0.09249506636175525;
+  constexpr T a61 = (T)5.86145544294642, a62 = (T)-12.92096931784711, a63 = (T)8.159367898576159,
+              a64 = (T)-0.071584973281401, a65 = (T)-0.028269050394068383;
+  constexpr T a71 = (T)0.09646076681806523, a72 = (T)0.01, a73 = (T)0.4798896504144996,
+              a74 = (T)1.379008574103742, a75 = (T)-3.290069515436081, a76 = (T)2.324710524099774;
+  T ys[N], f[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) k[0][i] = f0[i] * dt;
+#pragma unroll
+  for (int i = 0; i < N; ++i) ys[i] = y0[i] + (a21 * k[0][i]);
+  rhs(1, ys, f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) k[1][i] = f[i] * dt;
+#pragma unroll
+  for (int i = 0; i < N; ++i) ys[i] = y0[i] + (a31 * k[0][i] + a32 * k[1][i]);
+  rhs(2, ys, f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) k[2][i] = f[i] * dt;
+#pragma unroll
+  for (int i = 0; i < N; ++i) ys[i] = y0[i] + (a41 * k[0][i] + a42 * k[1][i] + a43 * k[2][i]);
+  rhs(3, ys, f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) k[3][i] = f[i] * dt;
+#pragma unroll
+  for (int i = 0; i < N; ++i) ys[i] = y0[i] + (a51 * k[0][i] + a52 * k[1][i] + a53 * k[2][i] + a54 * k[3][i]);
+  rhs(4, ys, f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) k[4][i] = f[i] * dt;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    ys[i] = y0[i] + (a61 * k[0][i] + a62 * k[1][i] + a63 * k[2][i] + a64 * k[3][i] + a65 * k[4][i]);
+  rhs(5, ys, f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) k[5][i] = f[i] * dt;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    ys[i] = y0[i] + (a71 * k[0][i] + a72 * k[1][i] + a73 * k[2][i] + a74 * k[3][i] + a75 * k[4][i] + a76 * k[5][i]);
+  rhs(6, ys, f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    k[6][i] = f[i] * dt;
+    y1[i] = ys[i];
+    f_last[i] = f[i];
+  }
+}
+
+// Dense-output weights b_i(theta) of diffrax's _Tsit5Interpolation.
+template <typename T>
+EX_HD void tsit5_dense_weights(T t, T *b) {
+  const T t2 = t * t;
+  b[0] = (T)-1.0530884977290216 * t * (t - (T)1.3299890189751412) * (t2 - (T)1.4364028541716351 * t + (T)0.7139816917074209);
+  b[1] = (T)0.1017 * t2 * (t2 - (T)2.1966568338249754 * t + (T)1.2949852507374631);
+  b[2] = (T)2.490627285651252793 * t2 * (t2 - (T)2.38535645472061657 * t + (T)1.57803468208092486);
+  b[3] = (T)-16.54810288924490272 * (t - (T)1.21712927295533244) * (t - (T)0.61620406037800089) * t2;
+  b[4] = (T)47.37952196281928122 * (t - (T)1.203071208372362603) * (t - (T)0.658047292653547382) * t2;
+  b[5] = (T)-34.87065786149660974 * (t - (T)1.2) * (t - (T)0.666666666666666667) * t2;
+  b[6] = (T)2.5 * (t - (T)1.0) * (t - (T)0.6) * t2;
+}
+
+}  // namespace exenv

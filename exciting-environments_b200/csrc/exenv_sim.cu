@@ -1,0 +1,512 @@
+// exenv_sim.cu -- vmap_sim_ahead as ONE persistent multi-step sm_100a kernel.
+//
+// Thread e of a CTA owns environment (blockIdx.x * E + e) for the whole trajectory: its ODE state, the Tsit5 FSAL
+// derivative and the stage increments stay in registers across all solver steps.  The batch-major API layout
+// (actions (B, T, A) in; observations (B, N+1, O) and D trajectory leaves (B, N+1) out -- reference
+// core_env.py:571-616) is bridged through shared-memory tiles of `tile_steps` solver steps:
+//
+//   load phase   : every warp walks environment rows and reads the tile's action span with lanes along time
+//                  (contiguous 128-byte segments), writing it transposed to smem as [time][env] (odd pitch, conflict free)
+//   in-place     : each thread de-normalises its own action column (PMSM: dq->alpha/beta, voltage-hexagon clip at
+//                  the advanced angle, dead-time shift -- pmsm_env.py:709-777)
+//   compute      : tile_steps solver steps per thread; every save is the solver's dense output evaluated at the
+//                  host-computed abscissa, wrapped / clipped, (PMSM: + torque) and staged to smem as [slot][env]
+//   store phase  : warps walk environment rows again with lanes along time and write each trajectory leaf,
+//                  the normalised observation rows and the optional reward / truncated / terminated outputs
+//                  (vmap_generate_rew_trunc_term_ahead, core_env.py:618-647) as contiguous row segments.
+//
+// All time arithmetic of diffrax.diffeqsolve (accumulated tnext, clip to t1, truncating ZOH index, linspace save grid,
+// dense-output abscissae) is environment independent; it is emulated once on the host in the plan dtype
+// (exenv_api.cu: build_schedule) and streamed to the kernel as one 64-bit word + dt per step and one theta per save.
+// PMSM flux maps are staged once per CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier).
+//
+// Algorithmic HBM traffic per env-step: S * (A + O + D) bytes.
+#include <cstdio>
+
+#include "exenv_kernel_common.cuh"
+#include "exenv_sim_core.cuh"
+
+namespace exenv {
+
+template <typename T>
+struct SimK {
+  long B, n_actions, n_save;
+  const T *sin[EXENV_MAX_PHYS];
+  const T *actions;
+  T *obs;
+  T *traj[EXENV_MAX_PHYS];
+  T *last[EXENV_MAX_PHYS];
+  T *klast[EXENV_MAX_ODE];
+  const T *ref[EXENV_MAX_PHYS];
+  T *reward;
+  uint8_t *trunc;
+  uint8_t *term;
+  const uint64_t *words;
+  const T *dts;
+  const T *thetas;
+  const SimTile *tiles;
+  int n_tiles, act_cap, save_cap;
+  int n_control;
+  int control[EXENV_MAX_CONTROL];
+  int deadtime;
+  T pmsm_adv, pmsm_lin_stop;  // (deadtime+0.5)*tau ; tau*(T-1) = linspace stop of pmsm_env.py:721
+  unsigned lut_bytes, lut_off_gy, lut_off_cells;
+  const void *lut_blob;
+  int lut_nx, lut_ny;
+  T lut_inv_dx, lut_inv_dy;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+
+template <class Env, int SOLVER, typename T, bool PER_ENV>
+__global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams<T> kp) {
+  constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
+  constexpr int NST = staged_values<Env>();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int E = blockDim.x, EP = E + 1;
+  const int e = threadIdx.x, lane = e & 31, warp = e >> 5, nwarps = E >> 5;
+  const long blk0 = (long)blockIdx.x * E;
+  const long b = blk0 + e;
+  const bool valid = b < a.B;
+  const int rows = (int)((a.B - blk0) < (long)E ? (a.B - blk0) : (long)E);  // valid environments in this CTA
+
+  T *sm_act = reinterpret_cast<T *>(smem_raw);               // [act_cap * A][EP]
+  T *sm_out = sm_act + (size_t)a.act_cap * A * EP;           // [save_cap * NST][EP]
+
+  typename Env::Aux aux{};
+  if constexpr (Env::IS_PMSM && Env::SATURATED) {
+    // stage the flux maps once per CTA: TMA bulk copy + mbarrier
+    size_t off = ((size_t)(a.act_cap * A + a.save_cap * NST) * EP * sizeof(T) + 15) & ~(size_t)15;
+    unsigned char *sm_lut = smem_raw + off;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut_bytes);
+    if (e == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(a.lut_bytes)
+                   : "memory");
+      tma_bulk_load(sm_lut, a.lut_blob, a.lut_bytes, mbar);
+    }
+    __syncthreads();
+    {
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(mbar))
+            : "memory");
+      }
+    }
+    aux.lut.gx = reinterpret_cast<const T *>(sm_lut);
+    aux.lut.gy = reinterpret_cast<const T *>(sm_lut + a.lut_off_gy);
+    aux.lut.cells = reinterpret_cast<const T *>(sm_lut + a.lut_off_cells);
+    aux.lut.nx = a.lut_nx;
+    aux.lut.ny = a.lut_ny;
+    aux.lut.inv_dx = a.lut_inv_dx;
+    aux.lut.inv_dy = a.lut_inv_dy;
+  }
+
+  // ---- per-environment constants and initial state
+  T pl[NP];
+  const T *p = kp.v;
+  if constexpr (PER_ENV) {
+    load_env_params<Env, T, true>(kp, valid ? b : 0, pl);
+    p = pl;
+  }
+  const T *an = p + Env::NSTATIC + 2 * D;
+  T s0[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) s0[d] = valid ? __ldg(a.sin[d] + b) : (T)0;
+  T y[NODE], f[NODE];
+  if constexpr (Env::IS_PMSM) {
+    y[0] = s0[3];
+    y[1] = s0[4];
+    y[2] = s0[2];
+    aux.omega_el = s0[6];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) y[i] = s0[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NODE; ++i) f[i] = (T)0;
+  bool have_f = false;
+  T last[NST];
+#pragma unroll
+  for (int i = 0; i < NST; ++i) last[i] = (T)0;
+  // dense-output weights at theta == 1 (the common save position), evaluated like any other theta
+  T bw1[7];
+  if constexpr (SOLVER == EXENV_TSIT5) tsit5_dense_weights<T>((T)1, bw1);
+
+  long save_idx = 0;
+  const int OW = O + a.n_control;
+  const bool epilogue = a.reward || a.trunc || a.term;
+  const int nt = trunc_dim<Env>(a.n_control);
+
+  for (int tile = 0; tile < a.n_tiles; ++tile) {
+    const SimTile ti = a.tiles[tile];
+    __syncthreads();  // previous store phase is done with both smem tiles
+
+    // ---- load phase: action span of this tile, [time][env] in smem -------------------------------------------
+    {
+      // PMSM: staged indices address the dead-time shifted sequence; entries below `deadtime` are the initial
+      // buffer (filled by the owner thread below), the rest map to raw action q - deadtime.
+      const int dead = Env::IS_PMSM ? a.deadtime : 0;
+      const int k0 = (ti.act_lo < dead) ? (dead - ti.act_lo) : 0;
+      const int n_el = (ti.act_cnt - k0) * A;
+      const long src_lo = (long)ti.act_lo + k0 - dead;
+      for (int r = warp; r < rows; r += nwarps) {
+        const T *src = a.actions + ((blk0 + r) * a.n_actions + src_lo) * A;
+        for (int j = lane; j < n_el; j += 32) sm_act[(size_t)(k0 * A + j) * EP + r] = __ldg(src + j);
+      }
+    }
+    __syncthreads();
+
+    if (valid) {
+      // ---- in place: normalised -> physical action, own column only -------------------------------------------
+      for (int k = 0; k < ti.act_cnt; ++k) {
+        T raw[A], u[A];
+#pragma unroll
+        for (int c = 0; c < A; ++c) raw[c] = sm_act[(size_t)(k * A + c) * EP + e];
+        prepare_action<Env, T>((long)ti.act_lo + k, raw, s0, p, a.deadtime, a.n_actions, a.pmsm_adv, a.pmsm_lin_stop,
+                               u);
+#pragma unroll
+        for (int c = 0; c < A; ++c) sm_act[(size_t)(k * A + c) * EP + e] = u[c];
+      }
+
+      // ---- compute phase --------------------------------------------------------------------------------------
+      const int n_end = ti.step_begin + ti.step_count;
+      uint64_t w_next = __ldg(a.words + ti.step_begin);
+      T dt_next = __ldg(a.dts + ti.step_begin);
+      for (int n = ti.step_begin; n < n_end; ++n) {
+        const uint64_t w = w_next;
+        const T dt = dt_next;
+        if (n + 1 < n_end) {
+          w_next = __ldg(a.words + n + 1);
+          dt_next = __ldg(a.dts + n + 1);
+        }
+        sim_one_step<Env, SOLVER, T>(
+            w, dt, y, f, have_f, p, aux, bw1, a.thetas, save_idx,
+            [&](int idx, T *u) {
+#pragma unroll
+              for (int c = 0; c < A; ++c) u[c] = sm_act[(size_t)((idx - ti.act_lo) * A + c) * EP + e];
+            },
+            [&](long sidx, const T *st) {
+              const int slot = (int)(sidx - ti.save_begin);
+#pragma unroll
+              for (int i = 0; i < NST; ++i) {
+                last[i] = st[i];
+                sm_out[(size_t)(slot * NST + i) * EP + e] = st[i];
+              }
+            });
+      }
+    } else {
+      save_idx += ti.save_cnt;
+    }
+    __syncthreads();
+
+    // ---- store phase: rows of the batch-major outputs, lanes along time ---------------------------------------
+    const int cnt = ti.save_cnt;
+    if (cnt > 0) {
+      // physical state field `d` of (row r, slot) from the staged values / action tile / inputs
+      auto field = [&](int d, int r, int slot) -> T {
+        if constexpr (Env::IS_PMSM) {
+          if (d == 2) return sm_out[(size_t)(slot * NST + 0) * EP + r];
+          if (d == 3) return sm_out[(size_t)(slot * NST + 1) * EP + r];
+          if (d == 4) return sm_out[(size_t)(slot * NST + 2) * EP + r];
+          if (d == 5) return sm_out[(size_t)(slot * NST + 3) * EP + r];
+          if (d == 6) return __ldg(a.sin[6] + blk0 + r);
+          // u_dq buffers over time: vstack([buffer]*deadtime, clipped actions); zeros when deadtime == 0
+          if (a.deadtime == 0) return (T)0;
+          const int k = ti.save_begin + slot - ti.act_lo;
+          return sm_act[(size_t)(k * 2 + d) * EP + r];
+        } else {
+          return sm_out[(size_t)(slot * NST + d) * EP + r];
+        }
+      };
+      for (int r = warp; r < rows; r += nwarps) {
+        const long br = blk0 + r;
+        T plr[NP];
+        const T *pr = kp.v;
+        if constexpr (PER_ENV) {
+          load_env_params<Env, T, true>(kp, br, plr);
+          pr = plr;
+        }
+        const long row0 = br * a.n_save + ti.save_begin;
+        // trajectory leaves
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          T *dst = a.traj[d];
+          if (dst) {
+            for (int k = lane; k < cnt; k += 32) dst[row0 + k] = field(d, r, k);
+          }
+        }
+        // observation rows: cnt * OW contiguous scalars
+        {
+          T *dst = a.obs + row0 * OW;
+          const int n_el = cnt * OW;
+          for (int j = lane; j < n_el; j += 32) {
+            const int k = j / OW, o = j - k * OW;
+            T val;
+            if (o < O) {
+              if constexpr (Env::IS_PMSM) {
+                T sv[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) sv[d] = (T)0;
+                // fetch only the field this entry needs
+                const int need = (o == 0) ? 3 : (o == 1) ? 4 : (o == 2) ? 6 : (o == 3) ? 5 : (o == 6) ? 0 : (o == 7) ? 1 : 2;
+                const T fv = field(need, r, k);
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                  if (d == need) sv[d] = fv;
+                val = obs_entry<Env, T>(o, sv, pr);
+              } else {
+                const T fv = field(o, r, k);
+                const T *pn = pr + Env::NSTATIC;
+                T mn = pn[0], mx = pn[1];
+#pragma unroll
+                for (int i = 1; i < D; ++i)
+                  if (o == i) {
+                    mn = pn[2 * i];
+                    mx = pn[2 * i + 1];
+                  }
+                val = norm_mm<T>(fv, mn, mx);
+              }
+            } else {
+              const int fld = a.control[o - O];
+              const T rv = __ldg(a.ref[fld] + br);
+              const T *pn = pr + Env::NSTATIC;
+              T mn = pn[0], mx = pn[1];
+#pragma unroll
+              for (int i = 1; i < D; ++i)
+                if (fld == i) {
+                  mn = pn[2 * i];
+                  mx = pn[2 * i + 1];
+                }
+              val = norm_mm<T>(rv, mn, mx);
+            }
+            dst[j] = val;
+          }
+        }
+        // fused reward / truncated / terminated (generate_rew_trunc_term_ahead): truncated for every saved
+        // state, reward / terminated for states[1:]
+        if (epilogue) {
+          for (int k = lane; k < cnt; k += 32) {
+            T sv[D], rf[D], ob[O + EXENV_MAX_CONTROL];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              sv[d] = field(d, r, k);
+              rf[d] = (a.n_control > 0) ? __ldg(a.ref[d] + br) : (T)0;
+            }
+            observe<Env, T>(sv, pr, ob);
+#pragma unroll
+            for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
+              if (j < a.n_control) ob[O + j] = norm_field<Env, T>(a.control[j], rf, pr);
+            const long gs = (long)ti.save_begin + k;  // global save index
+            bool t0 = false;
+#pragma unroll
+            for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
+              if (i < nt) {
+                const bool tv = trunc_entry<Env, T>(i, sv, ob, pr);
+                if (i == 0) t0 = tv;
+                if (a.trunc) a.trunc[(br * a.n_save + gs) * nt + i] = tv;
+              }
+            if (gs >= 1) {
+              const T rw = a.n_control > 0 ? reward_of<Env, T>(sv, rf, pr, a.n_control, a.control) : (T)0;
+              if (a.reward) a.reward[br * (a.n_save - 1) + gs - 1] = rw;
+              if (a.term) a.term[br * (a.n_save - 1) + gs - 1] = terminated_of<Env, T>(rw, t0);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- last_state (core_env.py:484-488) and the fresh solver.init derivative at (t1, y_last) --------------------
+  if (valid) {
+    T sl[D];
+    if constexpr (Env::IS_PMSM) {
+      const long dead_idx = a.n_save - 1;  // buffer leaf of the last saved state
+      const SimTile tl = a.tiles[a.n_tiles - 1];
+      sl[0] = sl[1] = (T)0;
+      if (a.deadtime > 0) {
+        const int k = (int)(dead_idx - tl.act_lo);
+        sl[0] = sm_act[(size_t)(k * 2) * EP + e];
+        sl[1] = sm_act[(size_t)(k * 2 + 1) * EP + e];
+      }
+      sl[2] = last[0];
+      sl[3] = last[1];
+      sl[4] = last[2];
+      sl[5] = last[3];
+      sl[6] = s0[6];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NODE; ++i) sl[i] = last[i];
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      if (a.last[d]) a.last[d][b] = sl[d];
+    if (SOLVER == EXENV_TSIT5 && a.klast[0]) {
+      // solver.init(term, t1, t1 + tau, y_last, args): derivative with the ZOH closure at t1 -> clamped last action
+      const SimTile tl = a.tiles[a.n_tiles - 1];
+      const int k = (int)(a.n_actions - 1 - tl.act_lo);
+      T u[A], yl[NODE], fi[NODE];
+#pragma unroll
+      for (int c = 0; c < A; ++c) u[c] = sm_act[(size_t)(k * A + c) * EP + e];
+      if constexpr (Env::IS_PMSM) {
+        yl[0] = last[1];
+        yl[1] = last[2];
+        yl[2] = last[0];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NODE; ++i) yl[i] = last[i];
+      }
+      Env::rhs(yl, u, p, aux, fi);
+#pragma unroll
+      for (int i = 0; i < NODE; ++i) a.klast[i][b] = fi[i];
+    }
+  }
+}
+
+// ---- launcher ----------------------------------------------------------------------------------------------------
+template <class Env, typename T>
+static size_t smem_bytes_t(const ExenvPlan &plan, int E, int act_cap, int save_cap) {
+  constexpr int NST = staged_values<Env>();
+  size_t n = (size_t)(act_cap * Env::A + save_cap * NST) * (E + 1) * sizeof(T);
+  if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) {
+    n = (n + 15) & ~(size_t)15;
+    n += plan.lut.bytes + 16;
+  }
+  return n;
+}
+
+template <class Env, int SOLVER, typename T, bool PER_ENV>
+static int launch_sim_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+  SimK<T> a{};
+  a.B = x.batch;
+  a.n_actions = x.n_actions;
+  a.n_save = sch.n_save;
+  for (int d = 0; d < Env::D; ++d) {
+    a.sin[d] = (const T *)x.state_in[d];
+    a.traj[d] = (T *)x.traj[d];
+    a.last[d] = (T *)x.last[d];
+    a.ref[d] = (const T *)x.ref[d];
+  }
+  for (int d = 0; d < Env::NODE; ++d) a.klast[d] = (T *)x.k_last[d];
+  a.actions = (const T *)x.actions;
+  a.obs = (T *)x.obs;
+  a.reward = (T *)x.reward;
+  a.trunc = x.truncated;
+  a.term = x.terminated;
+  a.words = sch.d_words;
+  a.dts = (const T *)sch.d_dt;
+  a.thetas = (const T *)sch.d_theta;
+  a.tiles = sch.d_tiles;
+  a.n_tiles = sch.n_tiles;
+  a.act_cap = sch.act_cap;
+  a.save_cap = sch.save_cap;
+  a.n_control = plan.desc.n_control;
+  for (int j = 0; j < EXENV_MAX_CONTROL; ++j) a.control[j] = plan.desc.control[j];
+  a.deadtime = plan.deadtime;
+  a.pmsm_adv = (T)plan.pmsm_adv;
+  a.pmsm_lin_stop = (T)(plan.desc.tau * (double)(x.n_actions - 1));
+  a.lut_bytes = (unsigned)plan.lut.bytes;
+  a.lut_off_gy = (unsigned)plan.lut.off_gy;
+  a.lut_off_cells = (unsigned)plan.lut.off_cells;
+  a.lut_blob = plan.lut.blob;
+  a.lut_nx = plan.lut.nx;
+  a.lut_ny = plan.lut.ny;
+  a.lut_inv_dx = (T)plan.lut.inv_dx;
+  a.lut_inv_dy = (T)plan.lut.inv_dy;
+  KParams<T> kp = make_kparams<T>(plan);
+  const int E = sim_block_envs(x.batch, x.block_envs);
+  const size_t smem = smem_bytes_t<Env, T>(plan, E, sch.act_cap, sch.save_cap);
+  auto kern = sim_kernel<Env, SOLVER, T, PER_ENV>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("sim_ahead needs %zu bytes of shared memory per CTA: %s", smem, cudaGetErrorString(e));
+      return EXENV_ERR_CUDA;
+    }
+  }
+  const unsigned grid = (unsigned)((x.batch + E - 1) / E);
+  kern<<<grid, E, smem, stream>>>(a, kp);
+  g_launch_count++;
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("exenv_sim_ahead launch failed: %s", cudaGetErrorString(e));
+    return EXENV_ERR_CUDA;
+  }
+  return EXENV_OK;
+}
+
+template <class Env, typename T>
+static int sim_dispatch2(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &s, cudaStream_t st) {
+  const bool tsit = plan.desc.solver == EXENV_TSIT5;
+  if constexpr (Env::IS_PMSM) {
+    return tsit ? launch_sim_t<Env, EXENV_TSIT5, T, false>(plan, x, s, st)
+                : launch_sim_t<Env, EXENV_EULER, T, false>(plan, x, s, st);
+  } else {
+    if (plan.per_env)
+      return tsit ? launch_sim_t<Env, EXENV_TSIT5, T, true>(plan, x, s, st)
+                  : launch_sim_t<Env, EXENV_EULER, T, true>(plan, x, s, st);
+    return tsit ? launch_sim_t<Env, EXENV_TSIT5, T, false>(plan, x, s, st)
+                : launch_sim_t<Env, EXENV_EULER, T, false>(plan, x, s, st);
+  }
+}
+
+template <typename T>
+static int sim_dispatch(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &s, cudaStream_t st) {
+  switch (plan.desc.env) {
+    case EXENV_PENDULUM: return sim_dispatch2<Pendulum<T>, T>(plan, x, s, st);
+    case EXENV_MASS_SPRING_DAMPER: return sim_dispatch2<MassSpringDamper<T>, T>(plan, x, s, st);
+    case EXENV_FLUID_TANK: return sim_dispatch2<FluidTank<T>, T>(plan, x, s, st);
+    case EXENV_CART_POLE: return sim_dispatch2<CartPole<T>, T>(plan, x, s, st);
+    case EXENV_ACROBOT: return sim_dispatch2<Acrobot<T>, T>(plan, x, s, st);
+    case EXENV_PMSM:
+      if (plan.desc.flags & EXENV_FLAG_SATURATED) return sim_dispatch2<Pmsm<T, true>, T>(plan, x, s, st);
+      return sim_dispatch2<Pmsm<T, false>, T>(plan, x, s, st);
+  }
+  set_error("unknown env %d", plan.desc.env);
+  return EXENV_ERR_INVALID;
+}
+
+int launch_sim(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream) {
+  return plan.desc.dtype == EXENV_F64 ? sim_dispatch<double>(plan, a, sch, stream)
+                                      : sim_dispatch<float>(plan, a, sch, stream);
+}
+
+template <typename T>
+static size_t smem_dispatch(const ExenvPlan &plan, int E, int ac, int sc) {
+  switch (plan.desc.env) {
+    case EXENV_PENDULUM: return smem_bytes_t<Pendulum<T>, T>(plan, E, ac, sc);
+    case EXENV_MASS_SPRING_DAMPER: return smem_bytes_t<MassSpringDamper<T>, T>(plan, E, ac, sc);
+    case EXENV_FLUID_TANK: return smem_bytes_t<FluidTank<T>, T>(plan, E, ac, sc);
+    case EXENV_CART_POLE: return smem_bytes_t<CartPole<T>, T>(plan, E, ac, sc);
+    case EXENV_ACROBOT: return smem_bytes_t<Acrobot<T>, T>(plan, E, ac, sc);
+    default: return smem_bytes_t<Pmsm<T, true>, T>(plan, E, ac, sc);
+  }
+}
+
+int sim_block_envs(int64_t batch, int requested) {
+  int E = requested > 0 ? ((requested + 31) / 32) * 32 : 128;
+  if (batch < E) E = (int)((batch + 31) / 32) * 32;
+  if (E < 32) E = 32;
+  if (E > 256) E = 256;
+  return E;
+}
+
+size_t sim_smem_bytes(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap) {
+  return plan.desc.dtype == EXENV_F64 ? smem_dispatch<double>(plan, block_envs, act_cap, save_cap)
+                                      : smem_dispatch<float>(plan, block_envs, act_cap, save_cap);
+}
+
+}  // namespace exenv

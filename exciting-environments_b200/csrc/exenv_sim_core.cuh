@@ -1,0 +1,134 @@
+// exenv_sim_core.cuh -- the per-environment body of the persistent sim_ahead kernel, free of any memory-layout
+// knowledge: action preparation (de-normalisation; PMSM voltage-hexagon clip + dead-time shift), one solver step
+// driven by a host-built schedule word, and the dense-output saves.  exenv_sim.cu wires it to shared-memory tiles;
+// tests/hostcheck compiles the very same functions for the CPU to validate them against the oracle without a GPU.
+#pragma once
+
+#include "../../include/exenv_b200.h"
+#include "exenv_envs.cuh"
+
+namespace exenv {
+
+// Schedule word (built by exenv_api.cu: build_schedule): bits 0-31 smallest ZOH action index of the step,
+// bits 32-45 seven 2-bit per-stage offsets from it, bits 46-49 number of saves falling into the step.
+EX_HD int sched_base(uint64_t w) { return (int)(unsigned)(w & 0xffffffffull); }
+EX_HD int sched_delta(uint64_t w, int stage) { return (int)((w >> (32 + 2 * stage)) & 3ull); }
+EX_HD int sched_saves(uint64_t w) { return (int)((w >> 46) & 15ull); }
+
+// Number of values staged per save: the post-processed ODE state (+ torque for PMSM: eps, i_d, i_q, torque).
+template <class Env>
+constexpr int staged_values() {
+  return Env::IS_PMSM ? 4 : Env::NODE;
+}
+
+// Physical action for index `q` of the zero-order-hold sequence the solver sees.
+//  generic envs : denormalize_action of raw action q                               (core_env.py:468)
+//  PMSM         : q < deadtime -> the initial u_dq buffer; else raw action j = q - deadtime clipped to the voltage
+//                 hexagon at eps_j = eps_0 + linspace(0, tau*(L-1), L)[j] * omega_el   (pmsm_env.py:709-777)
+// `raw` = normalised raw action (A values; ignored for buffer entries), s0 = initial physical state.
+template <class Env, typename T>
+EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, int deadtime, long n_actions, T pmsm_adv,
+                          T pmsm_lin_stop, T *u) {
+  const T *an = p + Env::NSTATIC + 2 * Env::D;
+  if constexpr (Env::IS_PMSM) {
+    if (q < deadtime) {
+      u[0] = s0[0];
+      u[1] = s0[1];
+    } else {
+      const long j = q - deadtime;
+      T lin;
+      if (n_actions == 1) lin = (T)0;
+      else if (j == n_actions - 1) lin = pmsm_lin_stop;
+      else lin = pmsm_lin_stop * ((T)j / (T)(n_actions - 1));
+      const T eps_j = s0[2] + lin * s0[6];
+      pmsm_clip<T>(raw[0], raw[1], eps_j, s0[6], p[5], pmsm_adv, an, &u[0], &u[1]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < Env::A; ++c) u[c] = denorm_mm<T>(raw[c], an[2 * c], an[2 * c + 1]);
+  }
+}
+
+// One solver step + its saves.
+//   y[NODE]      ODE state, updated in place
+//   f[NODE]      Tsit5 FSAL derivative carried between steps (have_f tells whether it is valid)
+//   fetch(idx,u) physical action of ZOH index idx (absolute)
+//   sink(save_index, staged[NST]) receives every saved sample, already wrapped / clipped (+ torque)
+//   thetas       dense-output abscissae, consumed in order starting at save_idx
+template <class Env, int SOLVER, typename T, class Fetch, class Sink>
+EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, typename Env::Aux &aux, const T *bw1,
+                        const T *thetas, long &save_idx, Fetch &&fetch, Sink &&sink) {
+  constexpr int NODE = Env::NODE, A = Env::A, NST = staged_values<Env>();
+  const int base = sched_base(w);
+  T y1[NODE], k[7][NODE];
+  if constexpr (SOLVER == EXENV_EULER) {  // diffrax.Euler
+    T u[A], f0[NODE];
+    fetch(base + sched_delta(w, 0), u);
+    Env::rhs(y, u, p, aux, f0);
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) {
+      k[0][i] = f0[i] * dt;
+      y1[i] = y[i] + k[0][i];
+    }
+  } else {  // diffrax.Tsit5 with FSAL
+    if (!have_f) {  // evaluated on diffrax's `first_step`
+      T u[A];
+      fetch(base + sched_delta(w, 0), u);
+      Env::rhs(y, u, p, aux, f);
+      have_f = true;
+    }
+    T fl[NODE];
+    tsit5_step<T, NODE>(
+        y, f, dt,
+        [&](int stage, const T *ys, T *fo) {
+          T u[A];
+          fetch(base + sched_delta(w, stage), u);
+          Env::rhs(ys, u, p, aux, fo);
+        },
+        y1, fl, k);
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) f[i] = fl[i];
+  }
+  // SaveAt(ts): dense output (LocalLinearInterpolation / _Tsit5Interpolation) at the scheduled abscissae
+  const int ns = sched_saves(w);
+  for (int q = 0; q < ns; ++q) {
+    const T th = thetas[save_idx];
+    T ysv[NODE];
+    if constexpr (SOLVER == EXENV_EULER) {
+#pragma unroll
+      for (int i = 0; i < NODE; ++i) ysv[i] = y[i] + th * (y1[i] - y[i]);
+    } else {
+      T bw[7];
+      if (th == (T)1) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) bw[j] = bw1[j];
+      } else {
+        tsit5_dense_weights<T>(th, bw);
+      }
+#pragma unroll
+      for (int i = 0; i < NODE; ++i) {
+        T acc = bw[0] * k[0][i];
+#pragma unroll
+        for (int j = 1; j < 7; ++j) acc += bw[j] * k[j][i];
+        ysv[i] = y[i] + acc;
+      }
+    }
+    Env::post(ysv);
+    T st[NST];
+    if constexpr (Env::IS_PMSM) {
+      st[0] = ysv[2];
+      st[1] = ysv[0];
+      st[2] = ysv[1];
+      st[3] = Env::torque(ysv[0], ysv[1], p, aux);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NODE; ++i) st[i] = ysv[i];
+    }
+    sink(save_idx, st);
+    ++save_idx;
+  }
+#pragma unroll
+  for (int i = 0; i < NODE; ++i) y[i] = y1[i];
+}
+
+}  // namespace exenv

@@ -1,0 +1,97 @@
+"""Shared test helpers: golden-vector loading, seeded synthetic inputs, ExenvDesc construction from an oracle
+configuration (so that CPU-only tests can drive the host-side schedule builder and the hostcheck harness)."""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+
+from oracle import oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = ROOT / "tests" / "golden" / "reference"
+GOLDEN_DIRS = {"pendulum": "pendulum", "mass_spring_damper": "mass_spring_damper", "fluid_tank": "fluid_tank",
+               "cart_pole": "cartpole", "acrobot": "acrobot", "pmsm": "pmsm"}
+ENVS = list(GOLDEN_DIRS)
+
+
+def load_golden(env):
+    d = GOLDEN / GOLDEN_DIRS[env]
+    props = json.load(open(d / "sim_properties.json"))
+    pn = {k: (v["min"], v["max"]) for k, v in props["physical_normalizations"].items()}
+    an = {k: (v["min"], v["max"]) for k, v in props["action_normalizations"].items()}
+    return dict(actions=np.load(d / "actions.npy"), observations=np.load(d / "observations.npy"),
+                static=props["params"], pn=pn, an=an, tau=props["tau"])
+
+
+def golden_oracle(env, solver=O.EULER, dtype=np.float64):
+    g = load_golden(env)
+    return O.Oracle(env, solver=solver, dtype=dtype, tau=g["tau"], static_params=g["static"],
+                    physical_normalizations=g["pn"], action_normalizations=g["an"]), g
+
+
+def random_state(orc, B, rng, spread=0.9):
+    """Physical state leaves drawn uniformly inside the normalisation box (SURVEY §8d synthetic inputs)."""
+    sp = orc.spec
+    leaves = []
+    for name in sp.phys:
+        lo, hi = orc.pn[name]
+        lo, hi = (np.asarray(lo, np.float64), np.asarray(hi, np.float64))
+        u = rng.uniform(-spread, spread, B)
+        if orc.env == "fluid_tank":
+            u = rng.uniform(0.0, 1.0, B) * 2 - 1
+        leaves.append(((u + 1) / 2 * (hi - lo) + lo).astype(orc.dtype))
+    if orc.env == "pmsm":  # currents inside the unit disc, buffers small, torque consistent is not required
+        r, phi = np.sqrt(rng.uniform(0, 0.8, B)), rng.uniform(0, 2 * np.pi, B)
+        i_max = 250.0 if orc.motor != "SEW" else 16.0
+        leaves[3] = (-np.abs(r * np.cos(phi)) * i_max).astype(orc.dtype)
+        leaves[4] = (r * np.sin(phi) * i_max).astype(orc.dtype)
+    return leaves
+
+
+def make_desc(orc, device_params=None):
+    """ExenvDesc for the product library from an oracle configuration.  Per-env arrays: `device_params` maps slot ->
+    device pointer (GPU tests) else host numpy pointers are used (hostcheck)."""
+    import exciting_environments_b200 as ex
+
+    L = ex._lib
+    d = L.ExenvDesc()
+    od = orc.desc
+    d.env, d.solver = od.env, od.solver
+    d.dtype = L.F64 if orc.dtype == np.float64 else L.F32
+    d.flags = L.FLAG_SATURATED if orc.saturated else 0
+    d.tau = orc.tau
+    d.n_control = od.n_control
+    for j in range(od.n_control):
+        d.control[j] = od.control[j]
+    d.time_rule = orc.time_rule
+    for i in range(32):
+        d.p[i] = od.p[i]
+        if od.pp[i]:
+            d.pp[i] = device_params[i] if device_params else od.pp[i]
+    return d
+
+
+def hc_lut(orc):
+    """HcLut struct (interleaved cells in the plan dtype) for the hostcheck harness."""
+    class HcLut(C.Structure):
+        _fields_ = [("gx", C.c_void_p), ("gy", C.c_void_p), ("cells", C.c_void_p), ("nx", C.c_int), ("ny", C.c_int),
+                    ("inv_dx", C.c_double), ("inv_dy", C.c_double)]
+
+    if not orc.saturated:
+        return None, []
+    gx, gy, maps = O.load_motor_lut(orc.motor)
+    cells = np.ascontiguousarray(np.transpose(maps, (1, 2, 0)), dtype=orc.dtype)
+    gxt, gyt = np.ascontiguousarray(gx, orc.dtype), np.ascontiguousarray(gy, orc.dtype)
+    h = HcLut(gxt.ctypes.data, gyt.ctypes.data, cells.ctypes.data, gx.size, gy.size, 1.0 / (gx[1] - gx[0]),
+              1.0 / (gy[1] - gy[0]))
+    return h, [gxt, gyt, cells]
+
+
+def ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def rel_err(a, b, floor=1e-30):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)) if a.size else 0.0

@@ -1,0 +1,152 @@
+// TEST-ONLY device-math host harness (never loaded by the product package).
+//
+// The per-environment device functions of the CUDA kernels (csrc/exenv_envs.cuh, exenv_sim_core.cuh,
+// exenv_kernel_common.cuh: env_step_one) are __host__ __device__; this file calls their HOST instantiations in plain
+// loops so that `pytest -m "not gpu"` can compare the kernels' arithmetic with the oracle on a machine without a GPU.
+// It is test infrastructure like oracle/: it shares no code path with `libexenv_b200.so`'s entry points and is built
+// into tests/hostcheck/_build/ by tests/conftest.py.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../exciting-environments_b200/csrc/exenv_kernel_common.cuh"
+#include "../../exciting-environments_b200/csrc/exenv_sim_core.cuh"
+
+using namespace exenv;
+
+namespace exenv {
+void set_error(const char *, ...) {}
+std::atomic<uint64_t> g_launch_count{0};
+}  // namespace exenv
+
+struct HcLut {
+  const void *gx, *gy, *cells;  // plan dtype, cells interleaved [(ix*ny+iy)*6+q]
+  int nx, ny;
+  double inv_dx, inv_dy;
+};
+
+template <typename T>
+static LutView<T> view(const HcLut *l) {
+  LutView<T> v{};
+  if (l && l->cells) {
+    v.gx = (const T *)l->gx;
+    v.gy = (const T *)l->gy;
+    v.cells = (const T *)l->cells;
+    v.nx = l->nx;
+    v.ny = l->ny;
+    v.inv_dx = (T)l->inv_dx;
+    v.inv_dy = (T)l->inv_dy;
+  }
+  return v;
+}
+
+template <class Env, int SOLVER, typename T>
+static void step_t(const ExenvDesc *d, const HcLut *lut, long B, const T *const *sin, const T *action, T *const *sout,
+                   T *obs, T *const *kout) {
+  constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O;
+  T p[EXENV_MAX_PARAMS];
+  for (long b = 0; b < B; ++b) {
+    for (int i = 0; i < EXENV_MAX_PARAMS; ++i) p[i] = d->pp[i] ? ((const T *)d->pp[i])[b] : (T)d->p[i];
+    T s[D], fl[NODE], ob[O];
+    for (int i = 0; i < D; ++i) s[i] = sin[i][b];
+    typename Env::Aux aux{};
+    if constexpr (Env::IS_PMSM) aux.lut = view<T>(lut);
+    const double dead = Env::IS_PMSM ? d->p[6] : 0.0;
+    env_step_one<Env, SOLVER, T>(s, action + b * A, p, aux, (T)d->tau, (T)((dead + 0.5) * d->tau), (int)dead, fl);
+    observe<Env, T>(s, p, ob);
+    for (int i = 0; i < D; ++i) sout[i][b] = s[i];
+    for (int i = 0; i < O; ++i) obs[b * O + i] = ob[i];
+    if (kout)
+      for (int i = 0; i < NODE; ++i) kout[i][b] = fl[i];
+  }
+}
+
+template <class Env, int SOLVER, typename T>
+static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, long n_save, long n_steps,
+                  const uint64_t *words, const double *dts, const double *thetas, const T *const *sin,
+                  const T *actions, T *const *traj /* NST leaves (B, n_save) */) {
+  constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, NST = staged_values<Env>();
+  std::vector<T> th(thetas, thetas + n_save);
+  const double dead_d = Env::IS_PMSM ? d->p[6] : 0.0;
+  const int dead = (int)dead_d;
+  for (long b = 0; b < B; ++b) {
+    T p[EXENV_MAX_PARAMS];
+    for (int i = 0; i < EXENV_MAX_PARAMS; ++i) p[i] = d->pp[i] ? ((const T *)d->pp[i])[b] : (T)d->p[i];
+    T s0[D];
+    for (int i = 0; i < D; ++i) s0[i] = sin[i][b];
+    typename Env::Aux aux{};
+    T y[NODE], f[NODE];
+    if constexpr (Env::IS_PMSM) {
+      aux.lut = view<T>(lut);
+      aux.omega_el = s0[6];
+      y[0] = s0[3];
+      y[1] = s0[4];
+      y[2] = s0[2];
+    } else {
+      for (int i = 0; i < NODE; ++i) y[i] = s0[i];
+    }
+    for (int i = 0; i < NODE; ++i) f[i] = 0;
+    bool have_f = false;
+    T bw1[7];
+    tsit5_dense_weights<T>((T)1, bw1);
+    long save_idx = 0;
+    const T adv = (T)((dead_d + 0.5) * d->tau), lin_stop = (T)(d->tau * (double)(n_actions - 1));
+    for (long n = 0; n < n_steps; ++n) {
+      sim_one_step<Env, SOLVER, T>(
+          words[n], (T)dts[n], y, f, have_f, p, aux, bw1, th.data(), save_idx,
+          [&](int idx, T *u) {
+            const long raw = (long)idx - dead;
+            const T *src = actions + (b * n_actions + (raw < 0 ? 0 : raw)) * A;
+            prepare_action<Env, T>(idx, src, s0, p, dead, n_actions, adv, lin_stop, u);
+          },
+          [&](long sidx, const T *st) {
+            for (int i = 0; i < NST; ++i) traj[i][b * n_save + sidx] = st[i];
+          });
+    }
+  }
+}
+
+#define DISPATCH(FUNC, ...)                                                                                     \
+  switch (d->env) {                                                                                             \
+    case EXENV_PENDULUM: tsit ? FUNC<Pendulum<T>, 1, T>(__VA_ARGS__) : FUNC<Pendulum<T>, 0, T>(__VA_ARGS__); break; \
+    case EXENV_MASS_SPRING_DAMPER:                                                                              \
+      tsit ? FUNC<MassSpringDamper<T>, 1, T>(__VA_ARGS__) : FUNC<MassSpringDamper<T>, 0, T>(__VA_ARGS__);       \
+      break;                                                                                                    \
+    case EXENV_FLUID_TANK: tsit ? FUNC<FluidTank<T>, 1, T>(__VA_ARGS__) : FUNC<FluidTank<T>, 0, T>(__VA_ARGS__); break; \
+    case EXENV_CART_POLE: tsit ? FUNC<CartPole<T>, 1, T>(__VA_ARGS__) : FUNC<CartPole<T>, 0, T>(__VA_ARGS__); break;   \
+    case EXENV_ACROBOT: tsit ? FUNC<Acrobot<T>, 1, T>(__VA_ARGS__) : FUNC<Acrobot<T>, 0, T>(__VA_ARGS__); break;       \
+    default:                                                                                                    \
+      if (d->flags & EXENV_FLAG_SATURATED)                                                                      \
+        tsit ? FUNC<Pmsm<T, true>, 1, T>(__VA_ARGS__) : FUNC<Pmsm<T, true>, 0, T>(__VA_ARGS__);                 \
+      else                                                                                                      \
+        tsit ? FUNC<Pmsm<T, false>, 1, T>(__VA_ARGS__) : FUNC<Pmsm<T, false>, 0, T>(__VA_ARGS__);               \
+  }
+
+template <typename T>
+static void step_any(const ExenvDesc *d, const HcLut *lut, long B, const void *const *sin, const void *action,
+                     void *const *sout, void *obs, void *const *kout) {
+  const bool tsit = d->solver == EXENV_TSIT5;
+  DISPATCH(step_t, d, lut, B, (const T *const *)sin, (const T *)action, (T *const *)sout, (T *)obs, (T *const *)kout)
+}
+template <typename T>
+static void sim_any(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, long n_save, long n_steps,
+                    const uint64_t *words, const double *dts, const double *thetas, const void *const *sin,
+                    const void *actions, void *const *traj) {
+  const bool tsit = d->solver == EXENV_TSIT5;
+  DISPATCH(sim_t, d, lut, B, n_actions, n_save, n_steps, words, dts, thetas, (const T *const *)sin, (const T *)actions,
+           (T *const *)traj)
+}
+
+extern "C" {
+void hc_step(const ExenvDesc *d, const HcLut *lut, long B, const void *const *sin, const void *action,
+             void *const *sout, void *obs, void *const *kout) {
+  if (d->dtype == EXENV_F64) step_any<double>(d, lut, B, sin, action, sout, obs, kout);
+  else step_any<float>(d, lut, B, sin, action, sout, obs, kout);
+}
+void hc_sim(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, long n_save, long n_steps,
+            const uint64_t *words, const double *dts, const double *thetas, const void *const *sin,
+            const void *actions, void *const *traj) {
+  if (d->dtype == EXENV_F64) sim_any<double>(d, lut, B, n_actions, n_save, n_steps, words, dts, thetas, sin, actions, traj);
+  else sim_any<float>(d, lut, B, n_actions, n_save, n_steps, words, dts, thetas, sin, actions, traj);
+}
+}

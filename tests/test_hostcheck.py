@@ -1,0 +1,133 @@
+"""CPU-only: the kernels' __host__ __device__ math (tests/hostcheck, host instantiation of csrc/*.cuh) and the
+host-side diffeqsolve schedule builder of libexenv_b200.so against the oracle.  The GPU parity tests proper are
+test_step_gpu.py / test_sim_gpu.py; this file makes sure the arithmetic and the time bookkeeping they rely on are
+right before GPU time is spent."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import ENVS, golden_oracle, hc_lut, make_desc, ptr_array, random_state, rel_err
+from oracle import oracle as O
+
+TOL = {np.float64: 1e-12, np.float32: 2e-6}
+
+
+def hc_step(lib, orc, state, action):
+    d = make_desc(orc)
+    lut, keep = hc_lut(orc)
+    B = state[0].shape[0]
+    out = [np.empty(B, orc.dtype) for _ in range(orc.D)]
+    obs = np.empty((B, orc.desc.n_obs), orc.dtype)
+    k = [np.empty(B, orc.dtype) for _ in range(orc.node)]
+    action = np.ascontiguousarray(action, orc.dtype)
+    lib.hc_step(C.byref(d), C.byref(lut) if lut else None, C.c_long(B), ptr_array(state),
+                C.c_void_p(action.ctypes.data), ptr_array(out), C.c_void_p(obs.ctypes.data), ptr_array(k))
+    return out, obs, k
+
+
+@pytest.mark.parametrize("env", ENVS)
+def test_device_math_replays_reference_golden_vectors(hostcheck_lib, env):
+    """Euler step of the kernel math, fp64, replayed over the reference's own golden trajectory
+    (reference tests/envs/<env>/test_<env>.py: test_step_results; tolerance rtol 1e-16 + atol 1e-8, PMSM rtol 1e-8)."""
+    orc, g = golden_oracle(env)
+    st = orc.reset(1, mode=2, values=g["observations"][0:1])["state"]
+    n = min(2000, g["actions"].shape[0])
+    gen = [g["observations"][0]]
+    for i in range(n):
+        st, obs, _ = hc_step(hostcheck_lib, orc, st, g["actions"][i:i + 1])
+        gen.append(obs[0])
+    gen = np.array(gen)
+    ref = g["observations"][: n + 1]
+    rtol = 1e-8 if env == "pmsm" else 1e-16
+    assert np.allclose(gen, ref, rtol=rtol, atol=1e-8)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("solver", [O.EULER, O.TSIT5])
+@pytest.mark.parametrize("env", ENVS + ["pmsm_brusa_sat", "pmsm_sew_sat"])
+def test_device_math_step_matches_oracle(hostcheck_lib, env, solver, dtype):
+    rng = np.random.default_rng(1234)
+    if env.startswith("pmsm_"):
+        orc = O.Oracle("pmsm", solver=solver, dtype=dtype, saturated=True, motor=env.split("_")[1].upper())
+    else:
+        orc = O.Oracle(env, solver=solver, dtype=dtype)
+    B = 257
+    st = random_state(orc, B, rng)
+    act = rng.uniform(-1, 1, (B, orc.A)).astype(dtype)
+    ref = orc.step(st, act)
+    out, obs, k = hc_step(hostcheck_lib, orc, st, act)
+    for a, b in zip(out, ref["state"]):
+        assert rel_err(a, b, floor=1e-3) < TOL[dtype] * 50
+    assert rel_err(obs, ref["obs"], floor=1e-3) < TOL[dtype] * 50
+    if solver == O.TSIT5:
+        for a, b in zip(k, ref["k"]):
+            assert rel_err(a, b, floor=1.0) < TOL[dtype] * 1e3
+
+
+def hc_sim(lib, orc, state, actions, obs_dt, act_dt, tile_steps=32):
+    import exciting_environments_b200 as ex
+
+    d = make_desc(orc)
+    lut, keep = hc_lut(orc)
+    B, T = actions.shape[0], actions.shape[1]
+    info, words, dt, theta, tiles = ex._lib.schedule(d, T, obs_dt, act_dt, tile_steps)
+    nst = 4 if orc.env == "pmsm" else orc.node
+    traj = [np.zeros((B, info.n_save), orc.dtype) for _ in range(nst)]
+    actions = np.ascontiguousarray(actions, orc.dtype)
+    lib.hc_sim(C.byref(d), C.byref(lut) if lut else None, C.c_long(B), C.c_long(T), C.c_long(info.n_save),
+               C.c_long(info.n_steps), C.c_void_p(words.ctypes.data), C.c_void_p(dt.ctypes.data),
+               C.c_void_p(theta.ctypes.data), ptr_array(state), C.c_void_p(actions.ctypes.data), ptr_array(traj))
+    return info, traj, (words, dt, theta, tiles)
+
+
+CASES = [
+    ("pendulum", 1e-4, 1e-4, 200), ("pendulum", 2e-2, 2e-2, 200), ("mass_spring_damper", 1e-4, 1e-4, 300),
+    ("fluid_tank", 1e-3, 1e-3, 150), ("cart_pole", 2e-2, 2e-2, 100), ("acrobot", 1e-3, 1e-3, 100),
+    ("pmsm", 1e-4, 1e-4, 120), ("pmsm_brusa_sat", 1e-4, 1e-4, 80), ("mass_spring_damper", 5e-5, 1e-4, 64),
+    ("pendulum", 1e-4, 3e-4, 40),
+]
+
+
+@pytest.mark.parametrize("time_rule", [0, 1])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("solver", [O.EULER, O.TSIT5])
+@pytest.mark.parametrize("env,obs_dt,act_dt,T", CASES)
+def test_schedule_and_sim_core_match_oracle(hostcheck_lib, env, obs_dt, act_dt, T, solver, dtype, time_rule):
+    """The product's host-built schedule (exenv_schedule_build) driving the kernel's per-step function reproduces the
+    oracle's independent, inline emulation of the diffeqsolve loop, including ZOH lag and fp32 time drift."""
+    rng = np.random.default_rng(99)
+    if env == "pmsm_brusa_sat":
+        orc = O.Oracle("pmsm", solver=solver, dtype=dtype, saturated=True, motor="BRUSA", time_rule=time_rule)
+    else:
+        orc = O.Oracle(env, solver=solver, dtype=dtype, time_rule=time_rule, tau=min(obs_dt, act_dt) if env != "pmsm" else obs_dt)
+    B = 33
+    st = random_state(orc, B, rng, spread=0.5)
+    acts = rng.uniform(-1, 1, (B, T, orc.A)).astype(dtype)
+    ref = orc.sim_ahead(st, acts, obs_dt, act_dt)
+    info, traj, _ = hc_sim(hostcheck_lib, orc, st, acts, obs_dt, act_dt)
+    assert info.n_steps == ref["n_steps"]
+    assert info.n_save == ref["obs"].shape[1]
+    if orc.env == "pmsm":
+        pairs = [(traj[0], ref["traj"][2]), (traj[1], ref["traj"][3]), (traj[2], ref["traj"][4]), (traj[3], ref["traj"][5])]
+    else:
+        pairs = list(zip(traj, ref["traj"]))
+    # chaotic envs amplify rounding differences along the horizon; tolerances are per-trajectory here, the per-step
+    # bound is checked in test_device_math_step_matches_oracle
+    tol = (1e-9 if dtype == np.float64 else 2e-3)
+    for a, b in pairs:
+        assert np.max(np.abs(a - b) / (1.0 + np.abs(b))) < tol
+
+
+def test_schedule_exposes_zoh_lag_and_fp32_drift():
+    """with accumulated time the truncating ZOH index lags for many steps."""
+    import exciting_environments_b200 as ex
+
+    orc = O.Oracle("pendulum", solver=O.EULER, dtype=np.float32)
+    info, words, dt, theta, tiles = ex._lib.schedule(make_desc(orc), 2000, 1e-4, 1e-4, 32)
+    base = (words & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    lag = np.sum(base != np.arange(info.n_steps).clip(max=1999))
+    assert lag > 100          # the index is not simply the step number in fp32
+    assert info.n_save == 2001
+    assert np.all((theta >= 0) & (theta <= 1))
+    assert tiles[:, 1].sum() == info.n_steps and tiles[:, 5].sum() == info.n_save
