@@ -90,7 +90,7 @@ SYMBOLS = [
 
 def build(verbose: bool = False) -> Path:
     """Compile every CUDA translation unit for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", str(_PKG / "csrc"), "-j4"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", str(_PKG / "csrc"), "-j8"], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode != 0:

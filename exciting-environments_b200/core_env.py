@@ -451,7 +451,9 @@ class CoreEnvironment:
         # broadcast leaves stay un-materialised (stride-0 views): reference, PRNGKey, solver_state, active flag
         def over_time(x):
             t = x if isinstance(x, torch.Tensor) else torch.as_tensor(x, device=dev)
-            return t.reshape(B, 1).expand(B, NS) if t.ndim >= 1 else t.expand(B, NS)
+            if t.ndim == 0:
+                return t.expand(B, NS)
+            return t.unsqueeze(1).expand(B, NS, *t.shape[1:])
 
         ref_t = [over_time(getattr(init_state.reference, n)) for n in self.PHYS_FIELDS]
         states = self.State(
@@ -467,8 +469,7 @@ class CoreEnvironment:
         # back in the floating dtype (the bool flag as 1.0)
         last_state = self.State(
             physical_state=self.PhysicalState(*last),
-            PRNGKey=torch.as_tensor(init_state.PRNGKey, device=dev).to(dt).expand(B) if not isinstance(
-                init_state.PRNGKey, torch.Tensor) else init_state.PRNGKey.to(dt),
+            PRNGKey=torch.as_tensor(init_state.PRNGKey, device=dev).to(dt),
             additions=self.Additions(solver_state=klast, active_solver_state=self._constant("one", B)),
             reference=self.PhysicalState(*[torch.as_tensor(getattr(init_state.reference, n), device=dev).to(dt)
                                            for n in self.PHYS_FIELDS]),

@@ -247,6 +247,14 @@ static int get_schedule(ExenvPlan *plan, int64_t n_actions, double obs_dt, doubl
   return EXENV_OK;
 }
 
+int sim_block_envs(int64_t batch, int requested) {
+  int E = requested > 0 ? ((requested + 31) / 32) * 32 : 128;
+  if (batch < E) E = (int)((batch + 31) / 32) * 32;
+  if (E < 32) E = 32;
+  if (E > 256) E = 256;
+  return E;
+}
+
 static bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace exenv

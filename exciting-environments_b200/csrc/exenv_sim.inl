@@ -1,4 +1,4 @@
-// exenv_sim.cu -- vmap_sim_ahead as ONE persistent multi-step sm_100a kernel.
+// exenv_sim.inl (included by exenv_sim_f32.cu / exenv_sim_f64.cu with EXENV_REAL / EXENV_SFX) -- vmap_sim_ahead as ONE persistent multi-step sm_100a kernel.
 //
 // Thread e of a CTA owns environment (blockIdx.x * E + e) for the whole trajectory: its ODE state, the Tsit5 FSAL
 // derivative and the stage increments stay in registers across all solver steps.  The batch-major API layout
@@ -25,6 +25,9 @@
 
 #include "exenv_kernel_common.cuh"
 #include "exenv_sim_core.cuh"
+
+#define EXENV_CAT_(a, b) a##b
+#define EXENV_CAT(a, b) EXENV_CAT_(a, b)
 
 namespace exenv {
 
@@ -479,9 +482,9 @@ static int sim_dispatch(const ExenvPlan &plan, const ExenvSimArgs &x, const SimS
   return EXENV_ERR_INVALID;
 }
 
-int launch_sim(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream) {
-  return plan.desc.dtype == EXENV_F64 ? sim_dispatch<double>(plan, a, sch, stream)
-                                      : sim_dispatch<float>(plan, a, sch, stream);
+int EXENV_CAT(launch_sim_, EXENV_SFX)(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch,
+                                       cudaStream_t stream) {
+  return sim_dispatch<EXENV_REAL>(plan, a, sch, stream);
 }
 
 template <typename T>
@@ -496,17 +499,8 @@ static size_t smem_dispatch(const ExenvPlan &plan, int E, int ac, int sc) {
   }
 }
 
-int sim_block_envs(int64_t batch, int requested) {
-  int E = requested > 0 ? ((requested + 31) / 32) * 32 : 128;
-  if (batch < E) E = (int)((batch + 31) / 32) * 32;
-  if (E < 32) E = 32;
-  if (E > 256) E = 256;
-  return E;
-}
-
-size_t sim_smem_bytes(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap) {
-  return plan.desc.dtype == EXENV_F64 ? smem_dispatch<double>(plan, block_envs, act_cap, save_cap)
-                                      : smem_dispatch<float>(plan, block_envs, act_cap, save_cap);
+size_t EXENV_CAT(sim_smem_bytes_, EXENV_SFX)(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap) {
+  return smem_dispatch<EXENV_REAL>(plan, block_envs, act_cap, save_cap);
 }
 
 }  // namespace exenv

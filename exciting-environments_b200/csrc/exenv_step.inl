@@ -1,4 +1,4 @@
-// exenv_step.cu -- vmap_step and vmap_reset state packing as sm_100a kernels.
+// exenv_step.inl (included by exenv_step_f32.cu / exenv_step_f64.cu with EXENV_REAL / EXENV_SFX) -- vmap_step and vmap_reset state packing as sm_100a kernels.
 //
 // step_kernel: one thread owns VEC consecutive environments (VEC = 16 bytes / sizeof(T)), so every state leaf
 // (B,), the action rows (B, A) and the observation rows (B, O) are moved with 128-bit coalesced accesses; the
@@ -11,8 +11,12 @@
 // Compiled with -fmad=false: the Euler path then reproduces the reference's golden vectors like un-contracted IEEE
 // arithmetic does (the kernel is bandwidth bound, contraction would buy nothing).
 #include <cstdio>
+#include <cstring>
 
 #include "exenv_kernel_common.cuh"
+
+#define EXENV_CAT_(a, b) a##b
+#define EXENV_CAT(a, b) EXENV_CAT_(a, b)
 
 namespace exenv {
 
@@ -34,15 +38,64 @@ struct StepK {
   T tau, pmsm_adv;
 };
 
-template <class Env, int SOLVER, typename T, bool PER_ENV, int VEC>
-__global__ void __launch_bounds__(256) step_kernel(const StepK<T> a, const KParams<T> kp, const LutView<T> lut) {
+// Contiguous byte run with the widest naturally aligned stores (N is a compile-time count, dst is N-aligned when N is
+// a power of two <= 16).
+template <int N>
+__device__ __forceinline__ void store_bytes(uint8_t *dst, const uint8_t *v) {
+  if constexpr (N % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 16; ++i) {
+      uint4 w;
+      memcpy(&w, v + 16 * i, 16);
+      reinterpret_cast<uint4 *>(dst)[i] = w;
+    }
+  } else if constexpr (N % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 8; ++i) {
+      uint2 w;
+      memcpy(&w, v + 8 * i, 8);
+      reinterpret_cast<uint2 *>(dst)[i] = w;
+    }
+  } else if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+      uint32_t w;
+      memcpy(&w, v + 4 * i, 4);
+      reinterpret_cast<uint32_t *>(dst)[i] = w;
+    }
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      uint16_t w;
+      memcpy(&w, v + 2 * i, 2);
+      reinterpret_cast<uint16_t *>(dst)[i] = w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = v[i];
+  }
+}
+
+// MODE 0: control_state == [] and no epilogue (plain vmap_step)            -> leanest register footprint
+// MODE 1: control_state == [] with the fused reward/truncated/terminated   -> GymWrapper default
+// MODE 2: generic (runtime n_control, runtime epilogue pointers, references; rows written with scalar stores)
+template <class Env, int SOLVER, typename T>
+constexpr int step_min_blocks() {
+  if (Env::IS_PMSM) return sizeof(T) == 4 ? 2 : 1;  // 7 state + 8 obs scalars per env: needs the registers
+  return SOLVER == EXENV_EULER ? (sizeof(T) == 4 ? 4 : 3) : (sizeof(T) == 4 ? 3 : 2);
+}
+
+template <class Env, int SOLVER, typename T, bool PER_ENV, int VEC, int MODE>
+__global__ void __launch_bounds__(256, step_min_blocks<Env, SOLVER, T>())
+    step_kernel(const StepK<T> a, const KParams<T> kp, const LutView<T> lut) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
+  constexpr int NT0 = trunc_dim<Env>(0);  // truncated width without reference entries
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t * VEC >= a.count) return;
   const long b0 = a.first + t * VEC;
 
-  // ---- coalesced 128-bit loads: D state leaves, A*VEC action scalars (+ references when tracked)
-  T s[VEC][D], act[VEC * A], ref[VEC][D];
+  // ---- coalesced 128-bit loads: D state leaves, A*VEC action scalars
+  T s[VEC][D], act[VEC * A];
   {
     T tmp[VEC];
 #pragma unroll
@@ -53,21 +106,11 @@ __global__ void __launch_bounds__(256) step_kernel(const StepK<T> a, const KPara
     }
 #pragma unroll
     for (int i = 0; i < A; ++i) vload<T, VEC>(a.action + b0 * A + i * VEC, act + i * VEC);
-    if (a.n_control > 0) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        vload<T, VEC>(a.ref[d] + b0, tmp);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) ref[v][d] = tmp[v];
-      }
-    }
   }
 
-  const int n_control = a.n_control;
-  const int OW = O + n_control;  // observation row width
-  T ob[VEC][O + EXENV_MAX_CONTROL], fl[VEC][NODE], rew[VEC];
-  uint8_t trc[VEC][O + EXENV_MAX_CONTROL], trm[VEC];
-  const bool epilogue = a.reward || a.trunc || a.term;
+  T ob[VEC * O], fl[VEC][NODE];
+  uint8_t trc[VEC * NT0], trm[VEC];
+  T rew[VEC];
 
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -80,17 +123,45 @@ __global__ void __launch_bounds__(256) step_kernel(const StepK<T> a, const KPara
     typename Env::Aux aux{};
     if constexpr (Env::IS_PMSM) aux.lut = lut;
     env_step_one<Env, SOLVER, T>(s[v], act + v * A, p, aux, a.tau, a.pmsm_adv, a.deadtime, fl[v]);
-    observe<Env, T>(s[v], p, ob[v]);
+    observe<Env, T>(s[v], p, ob + v * O);
+    if constexpr (MODE == 1) {
+      // control_state == []: reward is the constant 0 (reference: the Python int 0)
+      rew[v] = (T)0;
 #pragma unroll
-    for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
-      if (j < n_control) ob[v][O + j] = norm_field<Env, T>(a.control[j], ref[v], p);
-    if (epilogue) {
-      rew[v] = n_control > 0 ? reward_of<Env, T>(s[v], ref[v], p, n_control, a.control) : (T)0;
-      const int nt = trunc_dim<Env>(n_control);
+      for (int i = 0; i < NT0; ++i) trc[v * NT0 + i] = trunc_entry<Env, T>(i, s[v], ob + v * O, p);
+      trm[v] = terminated_of<Env, T>((T)0, trc[v * NT0] != 0);
+    }
+    if constexpr (MODE == 2) {
+      const int n_control = a.n_control;
+      const int OW = O + n_control;
+      const long b = b0 + v;
+      T full[O + EXENV_MAX_CONTROL], ref[D];
 #pragma unroll
-      for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
-        if (i < nt) trc[v][i] = trunc_entry<Env, T>(i, s[v], ob[v], p);
-      trm[v] = terminated_of<Env, T>(rew[v], trc[v][0] != 0);
+      for (int o = 0; o < O; ++o) full[o] = ob[v * O + o];
+      if (n_control > 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) ref[d] = __ldg(a.ref[d] + b);
+#pragma unroll
+        for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
+          if (j < n_control) full[O + j] = norm_field<Env, T>(a.control[j], ref, p);
+      }
+#pragma unroll
+      for (int o = 0; o < O + EXENV_MAX_CONTROL; ++o)
+        if (o < OW) a.obs[b * OW + o] = full[o];
+      if (a.reward || a.trunc || a.term) {
+        const T rw = n_control > 0 ? reward_of<Env, T>(s[v], ref, p, n_control, a.control) : (T)0;
+        const int nt = trunc_dim<Env>(n_control);
+        bool t0 = false;
+#pragma unroll
+        for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
+          if (i < nt) {
+            const bool tv = trunc_entry<Env, T>(i, s[v], full, p);
+            if (i == 0) t0 = tv;
+            if (a.trunc) a.trunc[b * nt + i] = tv;
+          }
+        if (a.reward) a.reward[b] = rw;
+        if (a.term) a.term[b] = terminated_of<Env, T>(rw, t0);
+      }
     }
   }
 
@@ -111,35 +182,14 @@ __global__ void __launch_bounds__(256) step_kernel(const StepK<T> a, const KPara
         vstore<T, VEC>(a.kout[d] + b0, tmp);
       }
     }
-    if (n_control == 0) {  // VEC * O contiguous scalars = O vectors
-      T flat[VEC * O];
+    if constexpr (MODE != 2) {  // VEC * O contiguous scalars = O vectors
 #pragma unroll
-      for (int v = 0; v < VEC; ++v)
-#pragma unroll
-        for (int o = 0; o < O; ++o) flat[v * O + o] = ob[v][o];
-#pragma unroll
-      for (int i = 0; i < O; ++i) vstore<T, VEC>(a.obs + b0 * O + i * VEC, flat + i * VEC);
-    } else {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v)
-#pragma unroll
-        for (int o = 0; o < O + EXENV_MAX_CONTROL; ++o)
-          if (o < OW) a.obs[(b0 + v) * OW + o] = ob[v][o];
+      for (int i = 0; i < O; ++i) vstore<T, VEC>(a.obs + b0 * O + i * VEC, ob + i * VEC);
     }
-    if (epilogue) {
+    if constexpr (MODE == 1) {
       if (a.reward) vstore<T, VEC>(a.reward + b0, rew);
-      const int nt = trunc_dim<Env>(n_control);
-      if (a.trunc) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-#pragma unroll
-          for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
-            if (i < nt) a.trunc[(b0 + v) * nt + i] = trc[v][i];
-      }
-      if (a.term) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) a.term[b0 + v] = trm[v];
-      }
+      if (a.trunc) store_bytes<VEC * NT0>(a.trunc + b0 * NT0, trc);
+      if (a.term) store_bytes<VEC>(a.term + b0, trm);
     }
   }
 }
@@ -262,7 +312,7 @@ static int launch_step_t(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStre
   a.reward = (T *)x.reward;
   a.trunc = x.truncated;
   a.term = x.terminated;
-  vec_ok &= aligned16(a.action) && aligned16(a.obs) && aligned16(a.reward);
+  vec_ok &= aligned16(a.action) && aligned16(a.obs) && aligned16(a.reward) && aligned16(a.trunc) && aligned16(a.term);
   a.n_control = plan.desc.n_control;
   for (int j = 0; j < EXENV_MAX_CONTROL; ++j) a.control[j] = plan.desc.control[j];
   a.deadtime = plan.deadtime;
@@ -272,19 +322,27 @@ static int launch_step_t(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStre
   const LutView<T> lut = make_lut_view<T>(plan);
   const long B = x.batch;
   const long n_vec = vec_ok ? (B / VEC) * VEC : 0;
+  const bool epi = a.reward || a.trunc || a.term;
   if (n_vec > 0) {
     a.first = 0;
     a.count = n_vec;
     const long threads = n_vec / VEC;
     const unsigned grid = (unsigned)((threads + 255) / 256);
-    step_kernel<Env, SOLVER, T, PER_ENV, VEC><<<grid, 256, 0, stream>>>(a, kp, lut);
+    if (PER_ENV || a.n_control > 0) {
+      step_kernel<Env, SOLVER, T, PER_ENV, VEC, 2><<<grid, 256, 0, stream>>>(a, kp, lut);
+    } else if constexpr (!PER_ENV) {
+      if (epi)
+        step_kernel<Env, SOLVER, T, false, VEC, 1><<<grid, 256, 0, stream>>>(a, kp, lut);
+      else
+        step_kernel<Env, SOLVER, T, false, VEC, 0><<<grid, 256, 0, stream>>>(a, kp, lut);
+    }
     g_launch_count++;
   }
   if (n_vec < B) {  // ragged tail or unaligned views: scalar accesses
     a.first = n_vec;
     a.count = B - n_vec;
     const unsigned grid = (unsigned)((a.count + 255) / 256);
-    step_kernel<Env, SOLVER, T, PER_ENV, 1><<<grid, 256, 0, stream>>>(a, kp, lut);
+    step_kernel<Env, SOLVER, T, PER_ENV, 1, 2><<<grid, 256, 0, stream>>>(a, kp, lut);
     g_launch_count++;
   }
   const cudaError_t e = cudaPeekAtLastError();
@@ -351,8 +409,8 @@ static int step_dispatch(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStre
   return EXENV_ERR_INVALID;
 }
 
-int launch_step(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream) {
-  return plan.desc.dtype == EXENV_F64 ? step_dispatch<double>(plan, a, stream) : step_dispatch<float>(plan, a, stream);
+int EXENV_CAT(launch_step_, EXENV_SFX)(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream) {
+  return step_dispatch<EXENV_REAL>(plan, a, stream);
 }
 
 template <class Env, typename T>
@@ -377,9 +435,8 @@ static int reset_dispatch(const ExenvPlan &plan, const ExenvResetArgs &x, cudaSt
   return EXENV_ERR_INVALID;
 }
 
-int launch_reset(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream) {
-  return plan.desc.dtype == EXENV_F64 ? reset_dispatch<double>(plan, a, stream)
-                                      : reset_dispatch<float>(plan, a, stream);
+int EXENV_CAT(launch_reset_, EXENV_SFX)(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream) {
+  return reset_dispatch<EXENV_REAL>(plan, a, stream);
 }
 
 }  // namespace exenv

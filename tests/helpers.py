@@ -30,7 +30,7 @@ def golden_oracle(env, solver=O.EULER, dtype=np.float64):
                     physical_normalizations=g["pn"], action_normalizations=g["an"]), g
 
 
-def random_state(orc, B, rng, spread=0.9):
+def random_state(orc, B, rng, spread=0.9, pmsm_gentle=False):
     """Physical state leaves drawn uniformly inside the normalisation box (SURVEY §8d synthetic inputs)."""
     sp = orc.spec
     leaves = []
@@ -46,6 +46,10 @@ def random_state(orc, B, rng, spread=0.9):
         i_max = 250.0 if orc.motor != "SEW" else 16.0
         leaves[3] = (-np.abs(r * np.cos(phi)) * i_max).astype(orc.dtype)
         leaves[4] = (r * np.sin(phi) * i_max).astype(orc.dtype)
+        if pmsm_gentle:  # low speed, small buffered voltages: currents stay inside the flux-map range for a while
+            leaves[6] = (leaves[6] * 0.02).astype(orc.dtype)
+            leaves[0] = (leaves[0] * 0.02).astype(orc.dtype)
+            leaves[1] = (leaves[1] * 0.02).astype(orc.dtype)
     return leaves
 
 
@@ -95,3 +99,27 @@ def ptr_array(arrs):
 def rel_err(a, b, floor=1e-30):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)) if a.size else 0.0
+
+
+def field_scales(orc):
+    """Half-span of every PhysicalState field's normalisation box (the natural unit of a state error)."""
+    out = []
+    for name in orc.spec.phys:
+        lo, hi = orc.pn[name]
+        out.append(float(np.max(np.abs(np.asarray(hi, np.float64) - np.asarray(lo, np.float64)))) / 2)
+    return out
+
+
+def scaled_err(a, b, scale):
+    """max |a - b| / max(|b|, scale): relative error with the field's normalisation half-span as the floor, so that
+    zero crossings of a state do not turn rounding noise into huge 'relative' errors."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), scale))) if a.size else 0.0
+
+
+def traj_err(a, b, scale):
+    """Trajectory error per environment, normalised by max(scale, max_t |b|) of that environment."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    denom = np.maximum(np.max(np.abs(b.reshape(b.shape[0], -1)), axis=1), scale)
+    err = np.max(np.abs(a - b).reshape(b.shape[0], -1), axis=1)
+    return float(np.max(err / denom))

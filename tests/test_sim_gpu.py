@@ -1,0 +1,234 @@
+"""`-m gpu`: vmap_sim_ahead (persistent multi-step kernel) through the C ABI against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import make_env, np_, to_state
+from helpers import ENVS, field_scales, random_state, traj_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _orc(env, solver, dtype, **kw):
+    if env.startswith("pmsm_"):
+        return O.Oracle("pmsm", solver=solver, dtype=dtype, saturated=True, motor=env.split("_")[1].upper(), **kw)
+    return O.Oracle(env, solver=solver, dtype=dtype, **kw)
+
+
+def _cmp(a, b, tol):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.max(np.abs(a - b) / (1.0 + np.abs(b))) < tol
+
+
+# Trajectory tolerances: 1e-4 relative (fp32) over the horizon as the north star states for the non-chaotic envs,
+# far tighter in fp64; errors are normalised per environment by max(normalisation half-span, max_t |x|)
+# (helpers.traj_err).  Rounding differences (libm, FMA contraction) are amplified by chaotic dynamics (cart-pole,
+# acrobot, pendulum at coarse tau) and by ill-conditioned ones (Euler at |1 + h*lambda| > 1 for the PMSM at speed;
+# saturated PMSM far outside its flux maps), so the bound is widened to 20x the trajectory's own sensitivity to a
+# one-ulp perturbation of the initial state, measured with the oracle.
+HORIZON_TOL = {np.float64: 1e-9, np.float32: 1e-4}
+
+
+def horizon_tol(orc, st, acts, dtype, ref, scales):
+    eps = np.finfo(dtype).eps
+    st2 = [(x * (1 + eps)).astype(dtype) for x in st]
+    pert = orc.sim_ahead(st2, acts, orc.tau, orc.tau)
+    sens = max(traj_err(p, r, s) for p, r, s in zip(pert["traj"], ref["traj"], scales))
+    return max(HORIZON_TOL[dtype], 20 * sens), sens
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("solver", [O.EULER, O.TSIT5])
+@pytest.mark.parametrize("env", ENVS + ["pmsm_brusa_sat", "pmsm_sew_sat"])
+def test_sim_ahead_matches_oracle(excenvs, env, solver, dtype):
+    rng = np.random.default_rng(42)
+    orc = _orc(env, solver, dtype)
+    B, T = 300, 200  # 3 CTAs, the last one ragged
+    gentle = orc.env == "pmsm"
+    st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=gentle)
+    acts = rng.uniform(-1, 1, (B, T, orc.A)).astype(dtype)
+    if gentle:
+        acts *= 0.02
+    ref = orc.sim_ahead(st, acts, orc.tau, orc.tau, epilogue=True)
+    e = make_env(excenvs, orc, B)
+    obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(
+        to_state(e, st), torch.as_tensor(acts, device="cuda"), orc.tau, orc.tau)
+    scales = field_scales(orc)
+    tol, sens = horizon_tol(orc, st, acts, dtype, ref, scales)
+    if gentle or orc.env in ("mass_spring_damper", "fluid_tank"):
+        assert tol == HORIZON_TOL[dtype], ("scenario is unexpectedly ill-conditioned", sens)
+    assert obs.shape == ref["obs"].shape
+    for name, b, s_ in zip(e.PHYS_FIELDS, ref["traj"], scales):
+        err = traj_err(np_(getattr(states.physical_state, name)), b, s_)
+        assert err <= tol, (name, err, tol)
+    ob, ob_ref = np_(obs), ref["obs"]
+    for o in range(orc.O):
+        err = traj_err(ob[..., o], ob_ref[..., o], 1.0)
+        assert err <= tol, ("obs", o, err, tol)
+    for name, b, s_ in zip(e.PHYS_FIELDS, ref["last"], scales):
+        assert np.array_equal(np_(getattr(last.physical_state, name)), np_(getattr(states.physical_state, name))[:, -1])
+    if solver == O.TSIT5:
+        ode = ("i_d", "i_q", "epsilon") if orc.env == "pmsm" else e.PHYS_FIELDS
+        for a, b, n in zip(last.additions.solver_state, ref["k_last"], ode):
+            s_ = scales[e.PHYS_FIELDS.index(n)]
+            err = traj_err((np_(a) * orc.tau)[:, None], (np.asarray(b, np.float64) * orc.tau)[:, None], s_)
+            assert err <= max(tol, 1e-5 if dtype == np.float32 else 1e-10) * 10, ("k_last", n, err)
+    # flags: bit exact wherever the oracle's observation is not within rounding distance of the threshold
+    tr_ref, tr = ref["truncated"], np_(trunc).astype(np.uint8)
+    if orc.n_trunc == orc.O:
+        safe = np.abs(np.abs(ref["obs"]) - 1.0) > max(1e-3, 100 * tol)
+        assert np.array_equal(tr[safe], tr_ref[safe])
+    else:
+        assert np.mean(tr == tr_ref) > 0.999
+    assert np.array_equal(np_(rew)[..., 0], ref["reward"])
+    assert rew.shape == (B, T, 1) and term.shape == (B, T, 1) and trunc.shape == (B, T + 1, orc.n_trunc)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("env", ["pmsm", "pmsm_brusa_sat"])
+def test_pmsm_open_loop_full_range_actions(excenvs, env, dtype):
+    """Full-range random voltages drive the currents far outside the permitted box (u / r_s ~ 15 kA); Euler at speed is
+    outside its stability region (|1 + h*lambda| ~ 1.03).  Compared with the sensitivity-scaled bound only."""
+    rng = np.random.default_rng(42)
+    for solver in (O.EULER, O.TSIT5):
+        orc = _orc(env, solver, dtype)
+        B, T = 300, 200
+        st = random_state(orc, B, rng, spread=0.5)
+        acts = rng.uniform(-1, 1, (B, T, 2)).astype(dtype)
+        ref = orc.sim_ahead(st, acts, orc.tau, orc.tau)
+        e = make_env(excenvs, orc, B)
+        obs, states, last = e.vmap_sim_ahead(to_state(e, st), torch.as_tensor(acts, device="cuda"), orc.tau, orc.tau)
+        scales = field_scales(orc)
+        tol, sens = horizon_tol(orc, st, acts, dtype, ref, scales)
+        for name, b, s_ in zip(e.PHYS_FIELDS, ref["traj"], scales):
+            err = traj_err(np_(getattr(states.physical_state, name)), b, s_)
+            assert err <= tol, (name, err, tol)
+
+
+@pytest.mark.parametrize("tile_steps,block_envs", [(1, 32), (7, 64), (16, 128), (64, 128), (32, 256)])
+def test_tile_geometry_does_not_change_results(excenvs, tile_steps, block_envs):
+    """Any (tile_steps, block_envs) staging must give bit-identical trajectories."""
+    rng = np.random.default_rng(5)
+    orc = O.Oracle("pendulum", solver=O.TSIT5, dtype=np.float32)
+    B, T = 777, 333
+    st = random_state(orc, B, rng)
+    acts = torch.as_tensor(rng.uniform(-1, 1, (B, T, 1)).astype(np.float32), device="cuda")
+    e = make_env(excenvs, orc, B)
+    base = e.vmap_sim_ahead(to_state(e, st), acts, 1e-4, 1e-4)
+    other = e.vmap_sim_ahead(to_state(e, st), acts, 1e-4, 1e-4, tile_steps=tile_steps, block_envs=block_envs)
+    assert torch.equal(base[0], other[0])
+    assert torch.equal(base[1].physical_state.theta, other[1].physical_state.theta)
+    assert torch.equal(base[2].physical_state.omega, other[2].physical_state.omega)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("obs_dt,act_dt,T", [(5e-5, 1e-4, 64), (1e-4, 3e-4, 50), (2e-2, 2e-2, 300), (1e-3, 1e-3, 1)])
+def test_zoh_and_save_grid_quirks(excenvs, obs_dt, act_dt, T, dtype):
+    """obs_stepsize < action_stepsize, coarse tau (ZOH lag), single action; time-varying actions."""
+    rng = np.random.default_rng(11)
+    orc = O.Oracle("mass_spring_damper", solver=O.TSIT5, dtype=dtype, tau=obs_dt)
+    B = 130
+    st = random_state(orc, B, rng)
+    acts = rng.uniform(-1, 1, (B, T, 1)).astype(dtype)
+    ref = orc.sim_ahead(st, acts, obs_dt, act_dt)
+    e = make_env(excenvs, orc, B)
+    obs, states, last = e.vmap_sim_ahead(to_state(e, st), torch.as_tensor(acts, device="cuda"), obs_dt, act_dt)
+    assert obs.shape == ref["obs"].shape
+    assert e.sim_ahead_shape(T, obs_dt, act_dt) == (ref["obs"].shape[1], ref["n_steps"])
+    assert _cmp(np_(obs), ref["obs"], HORIZON_TOL[dtype])
+
+
+def test_reference_tracking_per_env_params_and_epilogue(excenvs):
+    rng = np.random.default_rng(8)
+    B, T = 200, 60
+    base = O.Oracle("cart_pole", dtype=np.float32)
+    static = {k: (np.float64(v) * rng.uniform(0.9, 1.1, B)).astype(np.float32) for k, v in base.static.items()}
+    orc = O.Oracle("cart_pole", solver=O.TSIT5, dtype=np.float32, static_params=static, tau=1e-3,
+                   control_state=["theta", "velocity"])
+    st, refl = random_state(base, B, rng, 0.4), random_state(base, B, rng, 0.4)
+    acts = rng.uniform(-1, 1, (B, T, 1)).astype(np.float32)
+    ref = orc.sim_ahead(st, acts, 1e-3, 1e-3, ref=refl, epilogue=True)
+    e = make_env(excenvs, orc, B)
+    obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(
+        to_state(e, st, refl), torch.as_tensor(acts, device="cuda"), 1e-3, 1e-3)
+    assert obs.shape == (B, T + 1, 6)
+    assert _cmp(np_(obs), ref["obs"], 1e-4)
+    assert _cmp(np_(rew)[..., 0], ref["reward"], 1e-3)
+    assert np.mean(np_(term)[..., 0].astype(np.uint8) == ref["terminated"]) == 1.0
+
+
+def test_max_steps_mirrors_diffrax(excenvs):
+    """diffeqsolve's default max_steps=4096: > 4096 solver steps raise unless lifted."""
+    e = excenvs.MassSpringDamper(batch_size=32, dtype=torch.float32)
+    _, s = e.vmap_reset()
+    acts = torch.zeros((32, 5000, 1), device="cuda")
+    with pytest.raises(excenvs.ExenvError, match="maximum number of solver steps"):
+        e.vmap_sim_ahead(s, acts, e.tau, e.tau)
+    e.max_steps = None
+    obs, _, _ = e.vmap_sim_ahead(s, acts, e.tau, e.tau)
+    assert obs.shape == (32, 5001, 2)
+
+
+def test_euler_sim_ahead_equals_repeated_step(excenvs):
+    """reference tests/envs/test_core_functions.py:134-155 for every env (10 steps, all-ones actions, fp64)."""
+    for reg in excenvs.EnvironmentRegistry:
+        e = reg.make(batch_size=4, solver=excenvs.Euler(), dtype=torch.float64)
+        obs, state = e.vmap_reset()
+        acts = torch.ones((4, 10, e.action_dim), dtype=torch.float64, device="cuda")
+        obs_a, states_a, last_a = e.vmap_sim_ahead(state, acts, e.tau, e.tau)
+        last_obs = e.vmap_generate_observation(last_a)
+        for i in range(10):
+            obs_s, state = e.vmap_step(state, acts[:, i])
+        assert np.allclose(np_(last_obs), np_(obs_s), rtol=1e-16, atol=1e-8), reg
+        assert np.allclose(np_(obs_a[:, -1]), np_(obs_s), rtol=1e-16, atol=1e-8), reg
+
+
+def test_full_size_linearity_property(excenvs):
+    """BASELINE config 2 scale check with a size-independent property: the mass-spring-damper is linear, so the
+    trajectory of (c*x0, c*u) is c times the trajectory of (x0, u) -- checked on 2^17 envs x 2000 Tsit5 steps."""
+    B, T = 1 << 17, 2000
+    e = excenvs.MassSpringDamper(batch_size=B, solver=excenvs.Tsit5(), dtype=torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x0 = [torch.rand(B, device="cuda", generator=g) - 0.5 for _ in range(2)]
+    acts = torch.rand((B, T, 1), device="cuda", generator=g) * 0.5 - 0.25
+    s1 = e._new_state(x0, None, None, None, [None, None])
+    s2 = e._new_state([2 * x for x in x0], None, None, None, [None, None])
+    nan = torch.full((B,), float("nan"), device="cuda")
+    for s in (s1, s2):
+        s.PRNGKey = nan
+        s.reference = e.PhysicalState(nan, nan)
+    _, st1, _ = e.vmap_sim_ahead(s1, acts, 1e-4, 1e-4)
+    # action normalisation is affine with zero offset (min = -max), so scaling the normalised action scales the force
+    _, st2, _ = e.vmap_sim_ahead(s2, 2 * acts, 1e-4, 1e-4)
+    d = (st2.physical_state.deflection - 2 * st1.physical_state.deflection).abs().max().item()
+    v = (st2.physical_state.velocity - 2 * st1.physical_state.velocity).abs().max().item()
+    assert d < 1e-5 and v < 1e-4
+
+
+def test_host_buffer_entry_point_equals_device_entry_point(excenvs):
+    """exenv_sim_ahead_host (H2D / kernel / D2H pipeline over chunks) == exenv_sim_ahead."""
+    import ctypes as C
+
+    L = excenvs._lib
+    B, T = 1000, 120
+    e = excenvs.Pendulum(batch_size=B, solver=excenvs.Tsit5(), dtype=torch.float32)
+    _, s = e.vmap_reset(rng=1)
+    acts = torch.rand((B, T, 1), device="cuda") * 2 - 1
+    obs, states, last = e.vmap_sim_ahead(s, acts, e.tau, e.tau)
+    h_state = [getattr(s.physical_state, n).cpu().numpy().copy() for n in e.PHYS_FIELDS]
+    h_acts = acts.cpu().numpy().copy()
+    h_obs = np.zeros((B, T + 1, 2), np.float32)
+    h_traj = [np.zeros((B, T + 1), np.float32) for _ in range(2)]
+    h_last = [np.zeros(B, np.float32) for _ in range(2)]
+    a = L.ExenvSimArgs()
+    a.batch, a.n_actions, a.obs_stepsize, a.action_stepsize, a.max_steps = B, T, e.tau, e.tau, 4096
+    for i in range(2):
+        a.state_in[i] = h_state[i].ctypes.data
+        a.traj[i] = h_traj[i].ctypes.data
+        a.last[i] = h_last[i].ctypes.data
+    a.actions, a.obs = h_acts.ctypes.data, h_obs.ctypes.data
+    L.check(L.lib().exenv_sim_ahead_host(e._plan().handle, C.byref(a), 256))
+    assert np.array_equal(h_obs, np_(obs))
+    assert np.array_equal(h_traj[0], np_(states.physical_state.theta))
+    assert np.array_equal(h_last[1], np_(last.physical_state.omega))

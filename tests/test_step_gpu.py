@@ -1,0 +1,126 @@
+"""`-m gpu`: vmap_step through the C ABI (CUDA kernels) against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import make_env, np_, to_state
+from helpers import ENVS, field_scales, golden_oracle, random_state, scaled_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+# north_star tolerances: fp32 1e-6 relative per step, fp64 1e-12 per step.  "Relative" is measured against
+# max(|x|, half-span of the field's normalisation box) -- see helpers.scaled_err.
+TOL = {np.float64: 1e-12, np.float32: 1e-6}
+
+
+def _orc(env, solver, dtype, **kw):
+    if env.startswith("pmsm_"):
+        return O.Oracle("pmsm", solver=solver, dtype=dtype, saturated=True, motor=env.split("_")[1].upper(), **kw)
+    return O.Oracle(env, solver=solver, dtype=dtype, **kw)
+
+
+@pytest.mark.parametrize("env", ENVS)
+def test_golden_vectors_replayed_on_gpu(excenvs, env):
+    """reference tests/envs/<env>/test_<env>.py::test_step_results, kernel instead of JAX: fp64 Euler, closed loop,
+    same tolerance as the reference's own assertion (rtol 1e-16 + atol 1e-8; PMSM rtol 1e-8)."""
+    orc, g = golden_oracle(env)
+    e = make_env(excenvs, orc, 1)
+    obs0 = torch.as_tensor(g["observations"][0:1], dtype=torch.float64, device="cuda")
+    state = e.vmap_generate_state_from_observation(obs0)
+    acts = torch.as_tensor(g["actions"], dtype=torch.float64, device="cuda")
+    n = acts.shape[0]
+    out = torch.empty((n + 1, e.obs_dim), dtype=torch.float64, device="cuda")
+    out[0] = obs0[0]
+    for i in range(n):
+        obs, state = e.vmap_step(state, acts[i:i + 1])
+        out[i + 1] = obs[0]
+    gen = np_(out)
+    rtol = 1e-8 if env == "pmsm" else 1e-16
+    assert np.allclose(gen, g["observations"], rtol=rtol, atol=1e-8)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("solver", [O.EULER, O.TSIT5])
+@pytest.mark.parametrize("env", ENVS + ["pmsm_brusa_sat", "pmsm_sew_sat"])
+def test_step_matches_oracle(excenvs, env, solver, dtype):
+    rng = np.random.default_rng(1234)
+    orc = _orc(env, solver, dtype)
+    B = 4099  # 128-bit vector body + ragged scalar tail
+    st = random_state(orc, B, rng)
+    act = rng.uniform(-1, 1, (B, orc.A)).astype(dtype)
+    ref = orc.step(st, act, epilogue=True)
+    e = make_env(excenvs, orc, B)
+    obs, new, rew, trunc, term = e.vmap_step_with_epilogue(to_state(e, st), torch.as_tensor(act, device="cuda"))
+    sc = field_scales(orc)
+    for name, b, s_ in zip(e.PHYS_FIELDS, ref["state"], sc):
+        err = scaled_err(np_(getattr(new.physical_state, name)), b, s_)
+        assert err <= TOL[dtype], (name, err)
+    err = scaled_err(np_(obs), ref["obs"], 1.0)
+    assert err <= TOL[dtype], ("obs", err)
+    if solver == O.TSIT5:  # solver_state leaf: derivative, compared as the increment tau * k
+        ode_scale = [sc[e.PHYS_FIELDS.index(n)] for n in (("i_d", "i_q", "epsilon") if orc.env == "pmsm" else e.PHYS_FIELDS)]
+        for a, b, s_ in zip(new.additions.solver_state, ref["k"], ode_scale):
+            err = scaled_err(np_(a) * orc.tau, np.asarray(b, np.float64) * orc.tau, s_)
+            assert err <= TOL[dtype] * 10, ("k", err)
+    # flags are bit-exact
+    assert np.array_equal(np_(trunc).astype(np.uint8), ref["truncated"])
+    assert np.array_equal(np_(term)[:, 0].astype(np.uint8), ref["terminated"])
+    assert np.array_equal(np_(rew)[:, 0], ref["reward"])
+    assert bool(new.additions.active_solver_state.all())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("env", ["pendulum", "cart_pole", "acrobot", "mass_spring_damper", "fluid_tank"])
+def test_step_with_reference_tracking_and_per_env_parameters(excenvs, env, dtype):
+    """control_state + references (reward / terminated values) and (B,) parameter arrays (core_env.py:253-277)."""
+    rng = np.random.default_rng(7)
+    B = 1031
+    base = O.Oracle(env, dtype=dtype)
+    static = {k: (np.float64(v) * rng.uniform(0.9, 1.1, B)).astype(dtype) for k, v in base.static.items()}
+    pn = dict(base.pn)
+    first = base.spec.phys[0]
+    lo, hi = pn[first]
+    pn[first] = ((np.full(B, lo) * (1 + 0.05 * rng.uniform(0, 1, B)) - 0.01).astype(dtype),
+                 (np.full(B, hi) * (1 + 0.05 * rng.uniform(0, 1, B)) + 0.01).astype(dtype))
+    ctrl = list(base.spec.phys[:2])
+    orc = O.Oracle(env, solver=O.TSIT5, dtype=dtype, static_params=static, physical_normalizations=pn,
+                   control_state=ctrl)
+    st = random_state(base, B, rng)
+    ref_leaves = random_state(base, B, rng)
+    act = rng.uniform(-1, 1, (B, orc.A)).astype(dtype)
+    ref = orc.step(st, act, ref=ref_leaves, epilogue=True)
+    e = make_env(excenvs, orc, B)
+    assert e.in_axes_env_properties.static_params.__dict__[base.spec.static[0]] == 0
+    obs, new, rew, trunc, term = e.vmap_step_with_epilogue(to_state(e, st, ref_leaves),
+                                                           torch.as_tensor(act, device="cuda"))
+    assert obs.shape == (B, orc.O)
+    err = scaled_err(np_(obs), ref["obs"], 1.0)
+    assert err <= TOL[dtype], ("obs", err)
+    err = scaled_err(np_(rew)[:, 0], ref["reward"], 1.0)
+    assert err <= TOL[dtype] * 10, ("reward", err)
+    assert np.array_equal(np_(trunc).astype(np.uint8), ref["truncated"])
+    assert np.array_equal(np_(term)[:, 0].astype(np.uint8), ref["terminated"])
+
+
+def test_inplace_step_equals_out_of_place(excenvs):
+    e = excenvs.CartPole(batch_size=5000, solver=excenvs.Tsit5(), dtype=torch.float32)
+    _, s = e.vmap_reset(rng=3)
+    a = torch.rand((5000, 1), device="cuda") * 2 - 1
+    obs1, s1 = e.vmap_step(s, a)
+    keep = [getattr(s1.physical_state, n).clone() for n in e.PHYS_FIELDS]
+    obs2, s2 = e.vmap_step(s, a, inplace=True)
+    assert torch.equal(obs1, obs2)
+    for n, k in zip(e.PHYS_FIELDS, keep):
+        assert torch.equal(getattr(s2.physical_state, n), k)
+        assert getattr(s2.physical_state, n).data_ptr() == getattr(s.physical_state, n).data_ptr()
+
+
+def test_error_paths(excenvs):
+    e = excenvs.Pendulum(batch_size=8)
+    _, s = e.vmap_reset()
+    with pytest.raises(AssertionError):
+        e.vmap_step(s, torch.zeros((7, 1), device="cuda"))
+    with pytest.raises(ValueError):
+        excenvs.PMSM(batch_size=2, saturated=True)  # DEFAULT motor has no LUT (pmsm_env.py:189-193)
+    with pytest.raises(ValueError):
+        excenvs.Pendulum(batch_size=2, static_params={"g": [9.81, 9.81], "l": 2, "m": 1})  # list rejected

@@ -1,0 +1,86 @@
+"""Developer micro-benchmarks (not the driver's bench.py): device-timed throughput of the step and sim_ahead kernels
+over a few configurations, plus a tile-geometry sweep.  Prints one JSON object per line."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import exciting_environments_b200 as ex  # noqa: E402
+
+HBM = 6559.4e9
+
+
+def timed(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def bench_step(name, cls, solver, dtype, B):
+    env = cls(batch_size=B, solver=solver, dtype=dtype)
+    _, state = env.vmap_reset(rng=0)
+    S = 4 if dtype == torch.float32 else 8
+    D, A, O = env.physical_state_dim, env.action_dim, env.obs_dim
+    action = torch.rand((B, A), device="cuda", dtype=dtype) * 2 - 1
+    t = timed(lambda: env.vmap_step(state, action, inplace=True))
+    bytes_ = S * (2 * D + A + O + (env.N_ODE if isinstance(solver, ex.Tsit5) else 0)) * B
+    print(json.dumps(dict(kind="step", env=name, solver=repr(solver), dtype=str(dtype), B=B, ms=t * 1e3,
+                          env_steps_per_s=B / t, GBps=bytes_ / t / 1e9, frac_hbm=bytes_ / t / HBM)), flush=True)
+
+
+def bench_sim(name, cls, solver, dtype, B, T, tile_steps=0, block_envs=0, iters=3, **kw):
+    env = cls(batch_size=B, solver=solver, dtype=dtype, **kw)
+    env.max_steps = None
+    _, state = env.vmap_reset(rng=0)
+    S = 4 if dtype == torch.float32 else 8
+    D, A, O = env.physical_state_dim, env.action_dim, env.obs_dim
+    actions = torch.rand((B, T, A), device="cuda", dtype=dtype) * 2 - 1
+    obs = torch.empty((B, T + 1, O), device="cuda", dtype=dtype)
+    traj = [torch.empty((B, T + 1), device="cuda", dtype=dtype) for _ in range(D)]
+    out = dict(obs=obs, traj=traj)
+    t = timed(lambda: env._sim_impl(env.env_properties, B, state, actions, env.tau, env.tau, tile_steps=tile_steps,
+                                    block_envs=block_envs, out=out), warm=2, iters=iters)
+    bytes_ = S * (A + O + D) * B * T
+    print(json.dumps(dict(kind="sim", env=name, solver=repr(solver), dtype=str(dtype), B=B, T=T, tile=tile_steps,
+                          block=block_envs, ms=t * 1e3, env_steps_per_s=B * T / t, GBps=bytes_ / t / 1e9,
+                          frac_hbm=bytes_ / t / HBM)), flush=True)
+    del obs, traj, actions
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    f32, f64 = torch.float32, torch.float64
+    if what in ("all", "step"):
+        for name, cls in (("pendulum", ex.Pendulum), ("msd", ex.MassSpringDamper), ("tank", ex.FluidTank),
+                          ("cartpole", ex.CartPole), ("acrobot", ex.Acrobot), ("pmsm", ex.PMSM)):
+            for solver in (ex.Euler(), ex.Tsit5()):
+                for dt in (f32, f64):
+                    bench_step(name, cls, solver, dt, 1 << 24)
+        bench_step("pendulum", ex.Pendulum, ex.Euler(), f32, 1 << 26)
+    if what in ("all", "sweep"):
+        for tile in (8, 16, 32, 64):
+            for blk in (64, 128, 256):
+                try:
+                    bench_sim("msd", ex.MassSpringDamper, ex.Tsit5(), f32, 1 << 18, 500, tile, blk)
+                except Exception as e:  # smem limit
+                    print(json.dumps(dict(kind="sim", tile=tile, block=blk, error=str(e)[:100])), flush=True)
+    if what in ("all", "sim"):
+        bench_sim("msd", ex.MassSpringDamper, ex.Tsit5(), f32, 1 << 20, 2000, iters=2)
+        bench_sim("msd", ex.MassSpringDamper, ex.Euler(), f32, 1 << 20, 2000, iters=2)
+        bench_sim("msd", ex.MassSpringDamper, ex.Tsit5(), f64, 1 << 19, 2000, iters=2)
+        bench_sim("pendulum", ex.Pendulum, ex.Tsit5(), f32, 1 << 20, 1000, iters=2)
+        bench_sim("cartpole", ex.CartPole, ex.Tsit5(), f32, 1 << 22, 200, iters=2)
+        bench_sim("acrobot", ex.Acrobot, ex.Tsit5(), f32, 1 << 22, 200, iters=2)
+        bench_sim("pmsm", ex.PMSM, ex.Tsit5(), f32, 1 << 18, 1000, iters=2)
+        bench_sim("pmsm_sat", ex.PMSM, ex.Tsit5(), f32, 1 << 17, 1000, iters=2, saturated=True,
+                  motor_variant=ex.MotorVariant.BRUSA)
