@@ -105,6 +105,7 @@ static int build_schedule_t(const ExenvPlan &plan, int64_t n_actions, double obs
     int64_t base = idx[0];
     for (int s = 1; s < 7; ++s) base = std::min(base, idx[s]);
     uint64_t w = (uint64_t)(uint32_t)base;
+    int64_t dmax = 0;
     for (int s = 0; s < 7; ++s) {
       const int64_t d = idx[s] - base;
       if (d > 3) {
@@ -112,7 +113,9 @@ static int build_schedule_t(const ExenvPlan &plan, int64_t n_actions, double obs
         return EXENV_ERR_UNSUPPORTED;
       }
       w |= (uint64_t)d << (32 + 2 * s);
+      dmax = std::max(dmax, d);
     }
+    w |= (uint64_t)dmax << 50;
     int ns = 0;
     while (si <= N && ts[(size_t)si] <= tnext) {
       const T th = (tprev == tnext) ? (T)0 : (ts[(size_t)si] - tprev) / (tnext - tprev);
@@ -531,7 +534,7 @@ static int validate_sim(const ExenvPlan *plan, const ExenvSimArgs *a) {
 }
 
 static int prepare_sim(ExenvPlan *plan, const ExenvSimArgs *a, int *E_out, SimSchedule **sch) {
-  const int E = sim_block_envs(a->batch, a->block_envs);
+  const int E = 128;  // environments per CTA (compile-time constant of the sim kernel)
   int K = a->tile_steps > 0 ? a->tile_steps : auto_tile_steps(*plan, E);
   int rc = get_schedule(plan, a->n_actions, a->obs_stepsize, a->action_stepsize, K, true, sch);
   if (rc != EXENV_OK) return rc;

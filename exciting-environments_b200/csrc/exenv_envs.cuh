@@ -70,11 +70,22 @@ struct Pendulum {
   static constexpr int ID = 0, D = 2, NODE = 2, A = 1, O = 2, NSTATIC = 3, NTRUNC_BASE = 2;
   static constexpr bool IS_PMSM = false, SATURATED = false;
   using Aux = NoAux;
-  // :144-150  p = g, l, m
-  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+  struct Pre {
+    T lmg;
+    InvDiv<T> ml2;
+  };
+  EX_HD static Pre precompute(const T *p) {
     const T g = p[0], l = p[1], m = p[2];
+    Pre q;
+    q.lmg = l * m * g;
+    q.ml2 = make_invdiv<T>(m * (l * l));
+    return q;
+  }
+  // :144-150  p = g, l, m
+  template <bool FAST>
+  EX_HD static void rhs(const T *y, const T *u, const T *, const Pre &q, const Aux &, T *dy) {
     dy[0] = y[1];
-    dy[1] = (u[0] + l * m * g * Mth<T>::sin(y[0])) / (m * (l * l));
+    dy[1] = div_inv<FAST, T>(u[0] + q.lmg * Mth<T>::sin(y[0]), q.ml2);
   }
   EX_HD static void post(T *y) { y[0] = wrap_pi<T>(y[0]); }  // :188, :241
   EX_HD static bool is_angle(int f) { return f == 0; }
@@ -90,11 +101,20 @@ struct MassSpringDamper {
   static constexpr int ID = 1, D = 2, NODE = 2, A = 1, O = 2, NSTATIC = 3, NTRUNC_BASE = 2;
   static constexpr bool IS_PMSM = false, SATURATED = false;
   using Aux = NoAux;
+  struct Pre {
+    InvDiv<T> m;
+  };
+  EX_HD static Pre precompute(const T *p) {
+    Pre q;
+    q.m = make_invdiv<T>(p[2]);
+    return q;
+  }
   // :142-148  p = d, k, m
-  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
-    const T d = p[0], k = p[1], m = p[2];
+  template <bool FAST>
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &q, const Aux &, T *dy) {
+    const T d = p[0], k = p[1];
     dy[0] = y[1];
-    dy[1] = (u[0] - d * y[1] - k * y[0]) / m;
+    dy[1] = div_inv<FAST, T>(u[0] - d * y[1] - k * y[0], q.m);
   }
   EX_HD static void post(T *) {}
   EX_HD static bool is_angle(int) { return false; }
@@ -107,11 +127,23 @@ struct FluidTank {
   static constexpr int ID = 2, D = 1, NODE = 1, A = 1, O = 1, NSTATIC = 4, NTRUNC_BASE = 1;
   static constexpr bool IS_PMSM = false, SATURATED = false;
   using Aux = NoAux;
-  // :97-106  p = base_area, orifice_area, c_d, g
-  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+  struct Pre {
+    InvDiv<T> Ab;
+    T coef, two_g;
+  };
+  EX_HD static Pre precompute(const T *p) {
     const T Ab = p[0], Ao = p[1], cd = p[2], g = p[3];
+    Pre q;
+    q.Ab = make_invdiv<T>(Ab);
+    q.coef = cd * Ao / Ab;
+    q.two_g = (T)2 * g;
+    return q;
+  }
+  // :97-106  p = base_area, orifice_area, c_d, g
+  template <bool FAST>
+  EX_HD static void rhs(const T *y, const T *u, const T *, const Pre &q, const Aux &, T *dy) {
     const T h = y[0] < (T)0 ? (T)0 : y[0];
-    dy[0] = u[0] / Ab - cd * Ao / Ab * Mth<T>::sqrt((T)2 * g * h);
+    dy[0] = div_inv<FAST, T>(u[0], q.Ab) - q.coef * Mth<T>::sqrt(q.two_g * h);
   }
   EX_HD static void post(T *y) { y[0] = y[0] < (T)0 ? (T)0 : y[0]; }  // :146, :196
   EX_HD static bool is_angle(int) { return false; }
@@ -124,16 +156,27 @@ struct CartPole {
   static constexpr int ID = 3, D = 4, NODE = 4, A = 1, O = 4, NSTATIC = 6, NTRUNC_BASE = 4;
   static constexpr bool IS_PMSM = false, SATURATED = false;
   using Aux = NoAux;
+  struct Pre {
+    InvDiv<T> M, mpl;
+  };
+  EX_HD static Pre precompute(const T *p) {
+    Pre q;
+    q.M = make_invdiv<T>(p[4] + p[3]);
+    q.mpl = make_invdiv<T>(p[3] * p[2]);
+    return q;
+  }
   // :159-180  p = mu_p, mu_c, l, m_p, m_c, g ; y = deflection, velocity, theta, omega
-  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
-    const T mu_p = p[0], mu_c = p[1], l = p[2], m_p = p[3], m_c = p[4], g = p[5];
+  template <bool FAST>
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &q, const Aux &, T *dy) {
+    const T mu_p = p[0], mu_c = p[1], l = p[2], m_p = p[3], g = p[5];
     const T v = y[1], th = y[2], om = y[3];
     T s, c;
     Mth<T>::sincos(th, &s, &c);
     const T sg = sign_of<T>(v);
-    const T d_om = (g * s + c * ((-u[0] - m_p * l * (om * om) * s + mu_c * sg) / (m_c + m_p)) - (mu_p * om) / (m_p * l)) /
-                   (l * ((T)(4.0 / 3.0) - (m_p * (c * c)) / (m_c + m_p)));
-    const T d_v = (u[0] + m_p * l * ((om * om) * s - d_om * c) - mu_c * sg) / (m_c + m_p);
+    const T d_om = (g * s + c * div_inv<FAST, T>(-u[0] - q.mpl.d * (om * om) * s + mu_c * sg, q.M) -
+                    div_inv<FAST, T>(mu_p * om, q.mpl)) /
+                   (l * ((T)(4.0 / 3.0) - div_inv<FAST, T>(m_p * (c * c), q.M)));
+    const T d_v = div_inv<FAST, T>(u[0] + q.mpl.d * ((om * om) * s - d_om * c) - mu_c * sg, q.M);
     dy[0] = v;
     dy[1] = d_v;
     dy[2] = om;
@@ -154,7 +197,10 @@ struct Acrobot {
   static constexpr bool IS_PMSM = false, SATURATED = false;
   using Aux = NoAux;
   // :171-197  p = g, l_1, l_2, m_1, m_2, l_c1, l_c2, I_1, I_2 ; y = theta_1, theta_2, omega_1, omega_2
-  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &, T *dy) {
+  struct Pre {};
+  EX_HD static Pre precompute(const T *) { return Pre{}; }
+  template <bool FAST>
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &, const Aux &, T *dy) {
     const T g = p[0], l1 = p[1], m1 = p[3], m2 = p[4], lc1 = p[5], lc2 = p[6], I1 = p[7], I2 = p[8];
     const T th1 = y[0], th2 = y[1], om1 = y[2], om2 = y[3];
     T s2, c2;
@@ -196,13 +242,23 @@ struct Pmsm {
   static constexpr bool SATURATED = SAT;
   using Aux = PmsmAux<T>;
 
-  EX_HD static void rhs(const T *y, const T *u, const T *p, const Aux &aux, T *dy) {
+  struct Pre {
+    InvDiv<T> ld, lq;
+  };
+  EX_HD static Pre precompute(const T *p) {
+    Pre q;
+    q.ld = make_invdiv<T>(p[2]);
+    q.lq = make_invdiv<T>(p[3]);
+    return q;
+  }
+  template <bool FAST>
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &q_, const Aux &aux, T *dy) {
     const T r_s = p[1];
     const T id = y[0], iq = y[1], w = aux.omega_el;
     if constexpr (!SAT) {  // :509-523 linear_ode
       const T l_d = p[2], l_q = p[3], psi_p = p[4];
-      dy[0] = (u[0] + w * l_q * iq - r_s * id) / l_d;
-      dy[1] = (u[1] - w * (l_d * id + psi_p) - r_s * iq) / l_q;
+      dy[0] = div_inv<FAST, T>(u[0] + w * l_q * iq - r_s * id, q_.ld);
+      dy[1] = div_inv<FAST, T>(u[1] - w * (l_d * id + psi_p) - r_s * iq, q_.lq);
     } else {  // :487-507 nonlinear_ode
       T q[6];
       lut_eval<T, 0, 6>(aux.lut, id, iq, q);

@@ -70,6 +70,38 @@ EX_HD T denorm_mm(T z, T mn, T mx) {
   return (z + (T)1) / (T)2 * (mx - mn) + mn;
 }
 
+// Division by a loop-invariant divisor.  {d, r = RN(1/d)} is prepared once; q = RN(x*r), rem = x - d*q (exact, one
+// FMA), q' = RN(q + rem*r) is the correctly rounded x/d (Markstein) outside of the denormal / overflow corner cases
+// the full IEEE sequence guards with its slow path.  Used by the compute-bound sim_ahead kernel, where the plain
+// `/` costs ~13 instructions per use; the bandwidth-bound step kernels keep the plain operator.
+template <typename T>
+struct InvDiv {
+  T d, r;
+};
+template <typename T>
+EX_HD InvDiv<T> make_invdiv(T d) {
+  InvDiv<T> v;
+  v.d = d;
+  v.r = (T)1 / d;
+  return v;
+}
+EX_HD float fma_(float a, float b, float c) { return ::fmaf(a, b, c); }
+EX_HD double fma_(double a, double b, double c) { return ::fma(a, b, c); }
+template <bool FAST, typename T>
+EX_HD T div_inv(T x, const InvDiv<T> &c) {
+  if constexpr (FAST) {
+    const T q = x * c.r;
+    const T rem = fma_(-c.d, q, x);
+    return fma_(rem, c.r, q);
+  } else {
+    return x / c.d;
+  }
+}
+template <bool FAST, typename T>
+EX_HD T norm_inv(T x, T mn, const InvDiv<T> &span) {
+  return div_inv<FAST, T>((T)2 * (x - mn), span) - (T)1;
+}
+
 // jnp `%`: C fmod followed by the sign correction (jax.numpy.remainder); SURVEY Appendix A.
 template <typename T>
 EX_HD T pymod(T x, T y) {

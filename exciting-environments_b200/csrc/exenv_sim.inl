@@ -1,19 +1,23 @@
-// exenv_sim.inl (included by exenv_sim_f32.cu / exenv_sim_f64.cu with EXENV_REAL / EXENV_SFX) -- vmap_sim_ahead as ONE persistent multi-step sm_100a kernel.
+// exenv_sim.inl (included by exenv_sim_f32.cu / exenv_sim_f64.cu with EXENV_REAL / EXENV_SFX) -- vmap_sim_ahead as ONE
+// persistent multi-step sm_100a kernel.
 //
 // Thread e of a CTA owns environment (blockIdx.x * E + e) for the whole trajectory: its ODE state, the Tsit5 FSAL
 // derivative and the stage increments stay in registers across all solver steps.  The batch-major API layout
 // (actions (B, T, A) in; observations (B, N+1, O) and D trajectory leaves (B, N+1) out -- reference
 // core_env.py:571-616) is bridged through shared-memory tiles of `tile_steps` solver steps:
 //
-//   load phase   : every warp walks environment rows and reads the tile's action span with lanes along time
-//                  (contiguous 128-byte segments), writing it transposed to smem as [time][env] (odd pitch, conflict free)
+//   prefetch     : the action span of tile t+1 is copied global -> shared with cp.async (LDGSTS, 4/8-byte elements,
+//                  lanes along time = contiguous row segments in HBM, written transposed as [time][env] with an odd
+//                  pitch) while tile t is being integrated: double-buffered, no register staging, no exposed latency
 //   in-place     : each thread de-normalises its own action column (PMSM: dq->alpha/beta, voltage-hexagon clip at
 //                  the advanced angle, dead-time shift -- pmsm_env.py:709-777)
 //   compute      : tile_steps solver steps per thread; every save is the solver's dense output evaluated at the
 //                  host-computed abscissa, wrapped / clipped, (PMSM: + torque) and staged to smem as [slot][env]
-//   store phase  : warps walk environment rows again with lanes along time and write each trajectory leaf,
-//                  the normalised observation rows and the optional reward / truncated / terminated outputs
-//                  (vmap_generate_rew_trunc_term_ahead, core_env.py:618-647) as contiguous row segments.
+//   store phase  : warps walk environment rows with lanes along time and write each trajectory leaf and the
+//                  observation rows as contiguous segments; a lane keeps a fixed observation column, so its
+//                  normalisation constants (min, prepared reciprocal of the span) live in registers.  The optional
+//                  reward / truncated / terminated outputs (vmap_generate_rew_trunc_term_ahead, core_env.py:618-647),
+//                  reference entries and per-environment parameters take a generic (slower) row writer.
 //
 // All time arithmetic of diffrax.diffeqsolve (accumulated tnext, clip to t1, truncating ZOH index, linspace save grid,
 // dense-output abscissae) is environment independent; it is emulated once on the host in the plan dtype
@@ -30,6 +34,10 @@
 #define EXENV_CAT(a, b) EXENV_CAT_(a, b)
 
 namespace exenv {
+
+constexpr int SIM_E = 128;        // environments (threads) per CTA
+constexpr int SIM_EP = SIM_E + 1; // smem pitch of a [time][env] tile row (odd: conflict-free both ways)
+constexpr int SIM_NW = SIM_E / 32;
 
 template <typename T>
 struct SimK {
@@ -69,26 +77,232 @@ __device__ __forceinline__ void tma_bulk_load(void *dst_smem, const void *src_gm
                : "memory");
 }
 
+// Element-granular asynchronous copy global -> shared (SASS: LDGSTS).
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *dst_smem, const T *src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "n"(sizeof(T))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Issue the action span of one tile: rows = environments, lanes along the contiguous (time, action) axis.
+// PMSM: staged indices address the dead-time shifted sequence; entries below `deadtime` are the initial buffer
+// (filled by the owner thread later), the rest map to raw action q - deadtime.
+template <class Env, typename T>
+__device__ __forceinline__ void prefetch_actions(const SimK<T> &a, const SimTile &ti, T *sm_act, long blk0, int rows,
+                                                 int warp, int lane) {
+  constexpr int A = Env::A;
+  const int dead = Env::IS_PMSM ? a.deadtime : 0;
+  const int k0 = (ti.act_lo < dead) ? (dead - ti.act_lo) : 0;
+  const int n_el = (ti.act_cnt - k0) * A;
+  const long src_lo = (long)ti.act_lo + k0 - dead;
+  const T *src = a.actions + ((blk0 + warp) * a.n_actions + src_lo) * A;
+  const long row_stride = (long)SIM_NW * a.n_actions * A;
+  T *dst = sm_act + (size_t)(k0 * A) * SIM_EP + warp;
+  for (int r = warp; r < rows; r += SIM_NW) {
+    for (int j = lane; j < n_el; j += 32) cp_async_elem<T>(dst + (size_t)j * SIM_EP, src + j);
+    src += row_stride;
+    dst += SIM_NW;
+  }
+}
+
+// Physical-state field `d` of (row r, slot) from the staged values / action tile / inputs.
+template <class Env, typename T>
+__device__ __forceinline__ T staged_field(const SimK<T> &a, const SimTile &ti, const T *sm_act, const T *sm_out,
+                                          long blk0, int d, int r, int slot) {
+  constexpr int NST = staged_values<Env>();
+  if constexpr (Env::IS_PMSM) {
+    if (d == 2) return sm_out[(slot * NST + 0) * SIM_EP + r];
+    if (d == 3) return sm_out[(slot * NST + 1) * SIM_EP + r];
+    if (d == 4) return sm_out[(slot * NST + 2) * SIM_EP + r];
+    if (d == 5) return sm_out[(slot * NST + 3) * SIM_EP + r];
+    if (d == 6) return __ldg(a.sin[6] + blk0 + r);
+    // u_dq buffers over time: vstack([buffer]*deadtime, clipped actions); zeros when deadtime == 0
+    if (a.deadtime == 0) return (T)0;
+    const int k = ti.save_begin + slot - ti.act_lo;
+    return sm_act[(k * 2 + d) * SIM_EP + r];
+  } else {
+    return sm_out[(slot * NST + d) * SIM_EP + r];
+  }
+}
+
+// PMSM observation entry o -> PhysicalState field it reads (pmsm_env.py:905-916)
+__device__ __forceinline__ int pmsm_obs_field(int o) {
+  return (o == 0) ? 3 : (o == 1) ? 4 : (o == 2) ? 6 : (o == 3) ? 5 : (o == 6) ? 0 : (o == 7) ? 1 : 2;
+}
+
+// Fast row writer: control_state == [], no epilogue, shared parameters.
+template <class Env, typename T>
+__device__ __forceinline__ void store_tile_fast(const SimK<T> &a, const KParams<T> &kp, const SimTile &ti,
+                                                const T *sm_act, const T *sm_out, long blk0, int rows, int warp,
+                                                int lane) {
+  constexpr int D = Env::D, O = Env::O;
+  const int cnt = ti.save_cnt;
+  const T *pn = kp.v + Env::NSTATIC;
+  // ---- trajectory leaves: one contiguous run of `cnt` samples per (leaf, environment)
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    T *leaf = a.traj[d];
+    if (!leaf) continue;
+    T *dst = leaf + (blk0 + warp) * a.n_save + ti.save_begin;
+    const long stride = (long)SIM_NW * a.n_save;
+    for (int r = warp; r < rows; r += SIM_NW) {
+      for (int k = lane; k < cnt; k += 32) dst[k] = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, d, r, k);
+      dst += stride;
+    }
+  }
+  // ---- observation rows: cnt * O contiguous scalars; O divides 32, so a lane owns one observation column
+  {
+    constexpr int SPI = 32 / O;  // slots covered by one warp-wide store
+    const int o = lane & (O - 1), ks = lane / O;
+    int fld = o;
+    if constexpr (Env::IS_PMSM) fld = pmsm_obs_field(o);
+    T mn = pn[0];
+    T span = pn[1] - pn[0];
+#pragma unroll
+    for (int i = 1; i < D; ++i)
+      if (fld == i) {
+        mn = pn[2 * i];
+        span = pn[2 * i + 1] - pn[2 * i];
+      }
+    const InvDiv<T> sdiv = make_invdiv<T>(span);
+    T *dst = a.obs + ((blk0 + warp) * a.n_save + ti.save_begin) * O + lane;
+    const long stride = (long)SIM_NW * a.n_save * O;
+    for (int r = warp; r < rows; r += SIM_NW) {
+      int j = 0;
+      for (int k = ks; k < cnt; k += SPI, j += 32) {
+        const T v = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, fld, r, k);
+        T val;
+        if constexpr (Env::IS_PMSM) {
+          val = (o == 4) ? Mth<T>::cos(v) : (o == 5) ? Mth<T>::sin(v) : norm_inv<true, T>(v, mn, sdiv);
+        } else {
+          val = norm_inv<true, T>(v, mn, sdiv);
+        }
+        dst[j] = val;
+      }
+      dst += stride;
+    }
+  }
+}
+
+// Generic row writer: reference entries, per-environment parameters, fused reward / truncated / terminated.
+template <class Env, typename T, bool PER_ENV>
+__device__ __noinline__ void store_tile_generic(const SimK<T> &a, const KParams<T> &kp, const SimTile &ti,
+                                                const T *sm_act, const T *sm_out, long blk0, int rows, int warp,
+                                                int lane) {
+  constexpr int D = Env::D, O = Env::O, NP = num_params<Env>();
+  const int cnt = ti.save_cnt;
+  const int OW = O + a.n_control;
+  const bool epilogue = a.reward || a.trunc || a.term;
+  const int nt = trunc_dim<Env>(a.n_control);
+  for (int r = warp; r < rows; r += SIM_NW) {
+    const long br = blk0 + r;
+    T plr[NP];
+    const T *pr = kp.v;
+    if constexpr (PER_ENV) {
+      load_env_params<Env, T, true>(kp, br, plr);
+      pr = plr;
+    }
+    const T *pn = pr + Env::NSTATIC;
+    const long row0 = br * a.n_save + ti.save_begin;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      T *dst = a.traj[d];
+      if (dst)
+        for (int k = lane; k < cnt; k += 32) dst[row0 + k] = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, d, r, k);
+    }
+    {
+      T *dst = a.obs + row0 * OW;
+      const int n_el = cnt * OW;
+      for (int j = lane; j < n_el; j += 32) {
+        const int k = j / OW, o = j - k * OW;
+        T val;
+        if (o < O) {
+          int fld = o;
+          if constexpr (Env::IS_PMSM) fld = pmsm_obs_field(o);
+          const T fv = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, fld, r, k);
+          T mn = pn[0], mx = pn[1];
+#pragma unroll
+          for (int i = 1; i < D; ++i)
+            if (fld == i) {
+              mn = pn[2 * i];
+              mx = pn[2 * i + 1];
+            }
+          if (Env::IS_PMSM && o == 4) val = Mth<T>::cos(fv);
+          else if (Env::IS_PMSM && o == 5) val = Mth<T>::sin(fv);
+          else val = norm_mm<T>(fv, mn, mx);
+        } else {
+          const int fld = a.control[o - O];
+          const T rv = __ldg(a.ref[fld] + br);
+          T mn = pn[0], mx = pn[1];
+#pragma unroll
+          for (int i = 1; i < D; ++i)
+            if (fld == i) {
+              mn = pn[2 * i];
+              mx = pn[2 * i + 1];
+            }
+          val = norm_mm<T>(rv, mn, mx);
+        }
+        dst[j] = val;
+      }
+    }
+    // fused generate_rew_trunc_term_ahead: truncated for every saved state, reward / terminated for states[1:]
+    if (epilogue) {
+      for (int k = lane; k < cnt; k += 32) {
+        T sv[D], rf[D], ob[O + EXENV_MAX_CONTROL];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          sv[d] = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, d, r, k);
+          rf[d] = (a.n_control > 0) ? __ldg(a.ref[d] + br) : (T)0;
+        }
+        observe<Env, T>(sv, pr, ob);
+#pragma unroll
+        for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
+          if (j < a.n_control) ob[O + j] = norm_field<Env, T>(a.control[j], rf, pr);
+        const long gs = (long)ti.save_begin + k;  // global save index
+        bool t0 = false;
+#pragma unroll
+        for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
+          if (i < nt) {
+            const bool tv = trunc_entry<Env, T>(i, sv, ob, pr);
+            if (i == 0) t0 = tv;
+            if (a.trunc) a.trunc[(br * a.n_save + gs) * nt + i] = tv;
+          }
+        if (gs >= 1) {
+          const T rw = a.n_control > 0 ? reward_of<Env, T>(sv, rf, pr, a.n_control, a.control) : (T)0;
+          if (a.reward) a.reward[br * (a.n_save - 1) + gs - 1] = rw;
+          if (a.term) a.term[br * (a.n_save - 1) + gs - 1] = terminated_of<Env, T>(rw, t0);
+        }
+      }
+    }
+  }
+}
+
 template <class Env, int SOLVER, typename T, bool PER_ENV>
-__global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams<T> kp) {
-  constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
+__global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KParams<T> kp) {
+  constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, NP = num_params<Env>();
   constexpr int NST = staged_values<Env>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
-  const int E = blockDim.x, EP = E + 1;
-  const int e = threadIdx.x, lane = e & 31, warp = e >> 5, nwarps = E >> 5;
-  const long blk0 = (long)blockIdx.x * E;
+  const int e = threadIdx.x, lane = e & 31, warp = e >> 5;
+  const long blk0 = (long)blockIdx.x * SIM_E;
   const long b = blk0 + e;
   const bool valid = b < a.B;
-  const int rows = (int)((a.B - blk0) < (long)E ? (a.B - blk0) : (long)E);  // valid environments in this CTA
+  const int rows = (int)((a.B - blk0) < (long)SIM_E ? (a.B - blk0) : (long)SIM_E);  // valid environments here
 
-  T *sm_act = reinterpret_cast<T *>(smem_raw);               // [act_cap * A][EP]
-  T *sm_out = sm_act + (size_t)a.act_cap * A * EP;           // [save_cap * NST][EP]
+  const size_t act_elems = (size_t)a.act_cap * A * SIM_EP;
+  T *sm_act0 = reinterpret_cast<T *>(smem_raw);  // two [act_cap * A][EP] buffers
+  T *sm_out = sm_act0 + 2 * act_elems;           // [save_cap * NST][EP]
+
+  // first tile's actions are on their way while the constants below are set up
+  prefetch_actions<Env, T>(a, a.tiles[0], sm_act0, blk0, rows, warp, lane);
+  cp_async_commit();
 
   typename Env::Aux aux{};
   if constexpr (Env::IS_PMSM && Env::SATURATED) {
     // stage the flux maps once per CTA: TMA bulk copy + mbarrier
-    size_t off = ((size_t)(a.act_cap * A + a.save_cap * NST) * EP * sizeof(T) + 15) & ~(size_t)15;
+    size_t off = ((2 * act_elems + (size_t)a.save_cap * NST * SIM_EP) * sizeof(T) + 15) & ~(size_t)15;
     unsigned char *sm_lut = smem_raw + off;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut_bytes);
     if (e == 0) {
@@ -125,7 +339,7 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams
     load_env_params<Env, T, true>(kp, valid ? b : 0, pl);
     p = pl;
   }
-  const T *an = p + Env::NSTATIC + 2 * D;
+  const typename Env::Pre pre = Env::precompute(p);
   T s0[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) s0[d] = valid ? __ldg(a.sin[d] + b) : (T)0;
@@ -150,42 +364,35 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams
   if constexpr (SOLVER == EXENV_TSIT5) tsit5_dense_weights<T>((T)1, bw1);
 
   long save_idx = 0;
-  const int OW = O + a.n_control;
-  const bool epilogue = a.reward || a.trunc || a.term;
-  const int nt = trunc_dim<Env>(a.n_control);
+  const bool fast_store = !PER_ENV && a.n_control == 0 && !(a.reward || a.trunc || a.term);
 
   for (int tile = 0; tile < a.n_tiles; ++tile) {
     const SimTile ti = a.tiles[tile];
-    __syncthreads();  // previous store phase is done with both smem tiles
-
-    // ---- load phase: action span of this tile, [time][env] in smem -------------------------------------------
-    {
-      // PMSM: staged indices address the dead-time shifted sequence; entries below `deadtime` are the initial
-      // buffer (filled by the owner thread below), the rest map to raw action q - deadtime.
-      const int dead = Env::IS_PMSM ? a.deadtime : 0;
-      const int k0 = (ti.act_lo < dead) ? (dead - ti.act_lo) : 0;
-      const int n_el = (ti.act_cnt - k0) * A;
-      const long src_lo = (long)ti.act_lo + k0 - dead;
-      for (int r = warp; r < rows; r += nwarps) {
-        const T *src = a.actions + ((blk0 + r) * a.n_actions + src_lo) * A;
-        for (int j = lane; j < n_el; j += 32) sm_act[(size_t)(k0 * A + j) * EP + r] = __ldg(src + j);
-      }
+    T *sm_act = sm_act0 + (size_t)(tile & 1) * act_elems;
+    cp_async_wait_all();
+    __syncthreads();  // this tile's actions have landed; the previous store phase is done with sm_out / the other buffer
+    if (tile + 1 < a.n_tiles) {
+      prefetch_actions<Env, T>(a, a.tiles[tile + 1], sm_act0 + (size_t)((tile + 1) & 1) * act_elems, blk0, rows, warp,
+                               lane);
+      cp_async_commit();
     }
-    __syncthreads();
 
     if (valid) {
-      // ---- in place: normalised -> physical action, own column only -------------------------------------------
+      T *col = sm_act + e;  // this environment's column of the [time][env] tile
+      // ---- in place: normalised -> physical action ------------------------------------------------------------
       for (int k = 0; k < ti.act_cnt; ++k) {
         T raw[A], u[A];
 #pragma unroll
-        for (int c = 0; c < A; ++c) raw[c] = sm_act[(size_t)(k * A + c) * EP + e];
+        for (int c = 0; c < A; ++c) raw[c] = col[(k * A + c) * SIM_EP];
         prepare_action<Env, T>((long)ti.act_lo + k, raw, s0, p, a.deadtime, a.n_actions, a.pmsm_adv, a.pmsm_lin_stop,
                                u);
 #pragma unroll
-        for (int c = 0; c < A; ++c) sm_act[(size_t)(k * A + c) * EP + e] = u[c];
+        for (int c = 0; c < A; ++c) col[(k * A + c) * SIM_EP] = u[c];
       }
 
       // ---- compute phase --------------------------------------------------------------------------------------
+      const T *col0 = col - (long)ti.act_lo * A * SIM_EP;  // indexable by absolute ZOH index
+      T *out_col = sm_out + e - (long)ti.save_begin * NST * SIM_EP;
       const int n_end = ti.step_begin + ti.step_count;
       uint64_t w_next = __ldg(a.words + ti.step_begin);
       T dt_next = __ldg(a.dts + ti.step_begin);
@@ -197,17 +404,17 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams
           dt_next = __ldg(a.dts + n + 1);
         }
         sim_one_step<Env, SOLVER, T>(
-            w, dt, y, f, have_f, p, aux, bw1, a.thetas, save_idx,
+            w, dt, y, f, have_f, p, pre, aux, bw1, a.thetas, save_idx,
             [&](int idx, T *u) {
 #pragma unroll
-              for (int c = 0; c < A; ++c) u[c] = sm_act[(size_t)((idx - ti.act_lo) * A + c) * EP + e];
+              for (int c = 0; c < A; ++c) u[c] = col0[(idx * A + c) * SIM_EP];
             },
             [&](long sidx, const T *st) {
-              const int slot = (int)(sidx - ti.save_begin);
+              T *o = out_col + (long)sidx * NST * SIM_EP;
 #pragma unroll
               for (int i = 0; i < NST; ++i) {
                 last[i] = st[i];
-                sm_out[(size_t)(slot * NST + i) * EP + e] = st[i];
+                o[i * SIM_EP] = st[i];
               }
             });
       }
@@ -217,133 +424,29 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams
     __syncthreads();
 
     // ---- store phase: rows of the batch-major outputs, lanes along time ---------------------------------------
-    const int cnt = ti.save_cnt;
-    if (cnt > 0) {
-      // physical state field `d` of (row r, slot) from the staged values / action tile / inputs
-      auto field = [&](int d, int r, int slot) -> T {
-        if constexpr (Env::IS_PMSM) {
-          if (d == 2) return sm_out[(size_t)(slot * NST + 0) * EP + r];
-          if (d == 3) return sm_out[(size_t)(slot * NST + 1) * EP + r];
-          if (d == 4) return sm_out[(size_t)(slot * NST + 2) * EP + r];
-          if (d == 5) return sm_out[(size_t)(slot * NST + 3) * EP + r];
-          if (d == 6) return __ldg(a.sin[6] + blk0 + r);
-          // u_dq buffers over time: vstack([buffer]*deadtime, clipped actions); zeros when deadtime == 0
-          if (a.deadtime == 0) return (T)0;
-          const int k = ti.save_begin + slot - ti.act_lo;
-          return sm_act[(size_t)(k * 2 + d) * EP + r];
-        } else {
-          return sm_out[(size_t)(slot * NST + d) * EP + r];
-        }
-      };
-      for (int r = warp; r < rows; r += nwarps) {
-        const long br = blk0 + r;
-        T plr[NP];
-        const T *pr = kp.v;
-        if constexpr (PER_ENV) {
-          load_env_params<Env, T, true>(kp, br, plr);
-          pr = plr;
-        }
-        const long row0 = br * a.n_save + ti.save_begin;
-        // trajectory leaves
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          T *dst = a.traj[d];
-          if (dst) {
-            for (int k = lane; k < cnt; k += 32) dst[row0 + k] = field(d, r, k);
-          }
-        }
-        // observation rows: cnt * OW contiguous scalars
-        {
-          T *dst = a.obs + row0 * OW;
-          const int n_el = cnt * OW;
-          for (int j = lane; j < n_el; j += 32) {
-            const int k = j / OW, o = j - k * OW;
-            T val;
-            if (o < O) {
-              if constexpr (Env::IS_PMSM) {
-                T sv[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) sv[d] = (T)0;
-                // fetch only the field this entry needs
-                const int need = (o == 0) ? 3 : (o == 1) ? 4 : (o == 2) ? 6 : (o == 3) ? 5 : (o == 6) ? 0 : (o == 7) ? 1 : 2;
-                const T fv = field(need, r, k);
-#pragma unroll
-                for (int d = 0; d < D; ++d)
-                  if (d == need) sv[d] = fv;
-                val = obs_entry<Env, T>(o, sv, pr);
-              } else {
-                const T fv = field(o, r, k);
-                const T *pn = pr + Env::NSTATIC;
-                T mn = pn[0], mx = pn[1];
-#pragma unroll
-                for (int i = 1; i < D; ++i)
-                  if (o == i) {
-                    mn = pn[2 * i];
-                    mx = pn[2 * i + 1];
-                  }
-                val = norm_mm<T>(fv, mn, mx);
-              }
-            } else {
-              const int fld = a.control[o - O];
-              const T rv = __ldg(a.ref[fld] + br);
-              const T *pn = pr + Env::NSTATIC;
-              T mn = pn[0], mx = pn[1];
-#pragma unroll
-              for (int i = 1; i < D; ++i)
-                if (fld == i) {
-                  mn = pn[2 * i];
-                  mx = pn[2 * i + 1];
-                }
-              val = norm_mm<T>(rv, mn, mx);
-            }
-            dst[j] = val;
-          }
-        }
-        // fused reward / truncated / terminated (generate_rew_trunc_term_ahead): truncated for every saved
-        // state, reward / terminated for states[1:]
-        if (epilogue) {
-          for (int k = lane; k < cnt; k += 32) {
-            T sv[D], rf[D], ob[O + EXENV_MAX_CONTROL];
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-              sv[d] = field(d, r, k);
-              rf[d] = (a.n_control > 0) ? __ldg(a.ref[d] + br) : (T)0;
-            }
-            observe<Env, T>(sv, pr, ob);
-#pragma unroll
-            for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
-              if (j < a.n_control) ob[O + j] = norm_field<Env, T>(a.control[j], rf, pr);
-            const long gs = (long)ti.save_begin + k;  // global save index
-            bool t0 = false;
-#pragma unroll
-            for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
-              if (i < nt) {
-                const bool tv = trunc_entry<Env, T>(i, sv, ob, pr);
-                if (i == 0) t0 = tv;
-                if (a.trunc) a.trunc[(br * a.n_save + gs) * nt + i] = tv;
-              }
-            if (gs >= 1) {
-              const T rw = a.n_control > 0 ? reward_of<Env, T>(sv, rf, pr, a.n_control, a.control) : (T)0;
-              if (a.reward) a.reward[br * (a.n_save - 1) + gs - 1] = rw;
-              if (a.term) a.term[br * (a.n_save - 1) + gs - 1] = terminated_of<Env, T>(rw, t0);
-            }
-          }
-        }
+    if (ti.save_cnt > 0) {
+      if constexpr (!PER_ENV) {
+        if (fast_store)
+          store_tile_fast<Env, T>(a, kp, ti, sm_act, sm_out, blk0, rows, warp, lane);
+        else
+          store_tile_generic<Env, T, false>(a, kp, ti, sm_act, sm_out, blk0, rows, warp, lane);
+      } else {
+        store_tile_generic<Env, T, true>(a, kp, ti, sm_act, sm_out, blk0, rows, warp, lane);
       }
     }
   }
 
   // ---- last_state (core_env.py:484-488) and the fresh solver.init derivative at (t1, y_last) --------------------
   if (valid) {
+    const SimTile tl = a.tiles[a.n_tiles - 1];
+    const T *sm_act = sm_act0 + (size_t)((a.n_tiles - 1) & 1) * act_elems;
     T sl[D];
     if constexpr (Env::IS_PMSM) {
-      const long dead_idx = a.n_save - 1;  // buffer leaf of the last saved state
-      const SimTile tl = a.tiles[a.n_tiles - 1];
       sl[0] = sl[1] = (T)0;
       if (a.deadtime > 0) {
-        const int k = (int)(dead_idx - tl.act_lo);
-        sl[0] = sm_act[(size_t)(k * 2) * EP + e];
-        sl[1] = sm_act[(size_t)(k * 2 + 1) * EP + e];
+        const int k = (int)(a.n_save - 1 - tl.act_lo);  // buffer leaf of the last saved state
+        sl[0] = sm_act[(k * 2) * SIM_EP + e];
+        sl[1] = sm_act[(k * 2 + 1) * SIM_EP + e];
       }
       sl[2] = last[0];
       sl[3] = last[1];
@@ -359,11 +462,10 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams
       if (a.last[d]) a.last[d][b] = sl[d];
     if (SOLVER == EXENV_TSIT5 && a.klast[0]) {
       // solver.init(term, t1, t1 + tau, y_last, args): derivative with the ZOH closure at t1 -> clamped last action
-      const SimTile tl = a.tiles[a.n_tiles - 1];
       const int k = (int)(a.n_actions - 1 - tl.act_lo);
       T u[A], yl[NODE], fi[NODE];
 #pragma unroll
-      for (int c = 0; c < A; ++c) u[c] = sm_act[(size_t)(k * A + c) * EP + e];
+      for (int c = 0; c < A; ++c) u[c] = sm_act[(k * A + c) * SIM_EP + e];
       if constexpr (Env::IS_PMSM) {
         yl[0] = last[1];
         yl[1] = last[2];
@@ -372,7 +474,7 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams
 #pragma unroll
         for (int i = 0; i < NODE; ++i) yl[i] = last[i];
       }
-      Env::rhs(yl, u, p, aux, fi);
+      Env::template rhs<true>(yl, u, p, pre, aux, fi);
 #pragma unroll
       for (int i = 0; i < NODE; ++i) a.klast[i][b] = fi[i];
     }
@@ -381,9 +483,9 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimK<T> a, const KParams
 
 // ---- launcher ----------------------------------------------------------------------------------------------------
 template <class Env, typename T>
-static size_t smem_bytes_t(const ExenvPlan &plan, int E, int act_cap, int save_cap) {
+static size_t smem_bytes_t(const ExenvPlan &plan, int act_cap, int save_cap) {
   constexpr int NST = staged_values<Env>();
-  size_t n = (size_t)(act_cap * Env::A + save_cap * NST) * (E + 1) * sizeof(T);
+  size_t n = (size_t)(2 * act_cap * Env::A + save_cap * NST) * SIM_EP * sizeof(T);
   if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) {
     n = (n + 15) & ~(size_t)15;
     n += plan.lut.bytes + 16;
@@ -430,8 +532,7 @@ static int launch_sim_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimS
   a.lut_inv_dx = (T)plan.lut.inv_dx;
   a.lut_inv_dy = (T)plan.lut.inv_dy;
   KParams<T> kp = make_kparams<T>(plan);
-  const int E = sim_block_envs(x.batch, x.block_envs);
-  const size_t smem = smem_bytes_t<Env, T>(plan, E, sch.act_cap, sch.save_cap);
+  const size_t smem = smem_bytes_t<Env, T>(plan, sch.act_cap, sch.save_cap);
   auto kern = sim_kernel<Env, SOLVER, T, PER_ENV>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -440,8 +541,8 @@ static int launch_sim_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimS
       return EXENV_ERR_CUDA;
     }
   }
-  const unsigned grid = (unsigned)((x.batch + E - 1) / E);
-  kern<<<grid, E, smem, stream>>>(a, kp);
+  const unsigned grid = (unsigned)((x.batch + SIM_E - 1) / SIM_E);
+  kern<<<grid, SIM_E, smem, stream>>>(a, kp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
@@ -488,19 +589,20 @@ int EXENV_CAT(launch_sim_, EXENV_SFX)(const ExenvPlan &plan, const ExenvSimArgs 
 }
 
 template <typename T>
-static size_t smem_dispatch(const ExenvPlan &plan, int E, int ac, int sc) {
+static size_t smem_dispatch(const ExenvPlan &plan, int ac, int sc) {
   switch (plan.desc.env) {
-    case EXENV_PENDULUM: return smem_bytes_t<Pendulum<T>, T>(plan, E, ac, sc);
-    case EXENV_MASS_SPRING_DAMPER: return smem_bytes_t<MassSpringDamper<T>, T>(plan, E, ac, sc);
-    case EXENV_FLUID_TANK: return smem_bytes_t<FluidTank<T>, T>(plan, E, ac, sc);
-    case EXENV_CART_POLE: return smem_bytes_t<CartPole<T>, T>(plan, E, ac, sc);
-    case EXENV_ACROBOT: return smem_bytes_t<Acrobot<T>, T>(plan, E, ac, sc);
-    default: return smem_bytes_t<Pmsm<T, true>, T>(plan, E, ac, sc);
+    case EXENV_PENDULUM: return smem_bytes_t<Pendulum<T>, T>(plan, ac, sc);
+    case EXENV_MASS_SPRING_DAMPER: return smem_bytes_t<MassSpringDamper<T>, T>(plan, ac, sc);
+    case EXENV_FLUID_TANK: return smem_bytes_t<FluidTank<T>, T>(plan, ac, sc);
+    case EXENV_CART_POLE: return smem_bytes_t<CartPole<T>, T>(plan, ac, sc);
+    case EXENV_ACROBOT: return smem_bytes_t<Acrobot<T>, T>(plan, ac, sc);
+    default: return smem_bytes_t<Pmsm<T, true>, T>(plan, ac, sc);
   }
 }
 
 size_t EXENV_CAT(sim_smem_bytes_, EXENV_SFX)(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap) {
-  return smem_dispatch<EXENV_REAL>(plan, block_envs, act_cap, save_cap);
+  (void)block_envs;
+  return smem_dispatch<EXENV_REAL>(plan, act_cap, save_cap);
 }
 
 }  // namespace exenv

@@ -10,10 +10,12 @@
 namespace exenv {
 
 // Schedule word (built by exenv_api.cu: build_schedule): bits 0-31 smallest ZOH action index of the step,
-// bits 32-45 seven 2-bit per-stage offsets from it, bits 46-49 number of saves falling into the step.
+// bits 32-45 seven 2-bit per-stage offsets from it, bits 46-49 number of saves falling into the step,
+// bits 50-51 the largest of the seven offsets.
 EX_HD int sched_base(uint64_t w) { return (int)(unsigned)(w & 0xffffffffull); }
 EX_HD int sched_delta(uint64_t w, int stage) { return (int)((w >> (32 + 2 * stage)) & 3ull); }
 EX_HD int sched_saves(uint64_t w) { return (int)((w >> 46) & 15ull); }
+EX_HD int sched_dmax(uint64_t w) { return (int)((w >> 50) & 3ull); }  // largest stage offset of the step
 
 // Number of values staged per save: the post-processed ODE state (+ torque for PMSM: eps, i_d, i_q, torque).
 template <class Env>
@@ -52,29 +54,49 @@ EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, int dea
 // One solver step + its saves.
 //   y[NODE]      ODE state, updated in place
 //   f[NODE]      Tsit5 FSAL derivative carried between steps (have_f tells whether it is valid)
-//   fetch(idx,u) physical action of ZOH index idx (absolute)
+//   fetch(idx,u) physical action of ZOH index idx (absolute); called once per distinct index of the step
 //   sink(save_index, staged[NST]) receives every saved sample, already wrapped / clipped (+ torque)
 //   thetas       dense-output abscissae, consumed in order starting at save_idx
+// Divisions by parameter-only denominators use the prepared reciprocals (div_inv<true>), see exenv_math.cuh.
 template <class Env, int SOLVER, typename T, class Fetch, class Sink>
-EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, typename Env::Aux &aux, const T *bw1,
-                        const T *thetas, long &save_idx, Fetch &&fetch, Sink &&sink) {
+EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, const typename Env::Pre &pre,
+                        typename Env::Aux &aux, const T *bw1, const T *thetas, long &save_idx, Fetch &&fetch,
+                        Sink &&sink) {
   constexpr int NODE = Env::NODE, A = Env::A, NST = staged_values<Env>();
   const int base = sched_base(w);
   T y1[NODE], k[7][NODE];
   if constexpr (SOLVER == EXENV_EULER) {  // diffrax.Euler
     T u[A], f0[NODE];
     fetch(base + sched_delta(w, 0), u);
-    Env::rhs(y, u, p, aux, f0);
+    Env::template rhs<true>(y, u, p, pre, aux, f0);
 #pragma unroll
     for (int i = 0; i < NODE; ++i) {
       k[0][i] = f0[i] * dt;
       y1[i] = y[i] + k[0][i];
     }
   } else {  // diffrax.Tsit5 with FSAL
+    // the (at most four) distinct ZOH actions of this step, then a warp-uniform select per stage
+    T ua[4][A];
+    const int dmax = sched_dmax(w);
+    fetch(base, ua[0]);
+#pragma unroll
+    for (int d = 1; d < 4; ++d) {
+      if (d <= dmax) {
+        fetch(base + d, ua[d]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < A; ++c) ua[d][c] = ua[0][c];
+      }
+    }
+    auto stage_u = [&](int stage, T *u) {
+      const int d = sched_delta(w, stage);
+#pragma unroll
+      for (int c = 0; c < A; ++c) u[c] = d == 0 ? ua[0][c] : (d == 1 ? ua[1][c] : (d == 2 ? ua[2][c] : ua[3][c]));
+    };
     if (!have_f) {  // evaluated on diffrax's `first_step`
       T u[A];
-      fetch(base + sched_delta(w, 0), u);
-      Env::rhs(y, u, p, aux, f);
+      stage_u(0, u);
+      Env::template rhs<true>(y, u, p, pre, aux, f);
       have_f = true;
     }
     T fl[NODE];
@@ -82,8 +104,8 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, 
         y, f, dt,
         [&](int stage, const T *ys, T *fo) {
           T u[A];
-          fetch(base + sched_delta(w, stage), u);
-          Env::rhs(ys, u, p, aux, fo);
+          stage_u(stage, u);
+          Env::template rhs<true>(ys, u, p, pre, aux, fo);
         },
         y1, fl, k);
 #pragma unroll

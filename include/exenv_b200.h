@@ -156,7 +156,7 @@ typedef struct ExenvSimArgs {
   uint8_t *truncated;  /* optional (B, N+1, n_trunc) */
   uint8_t *terminated; /* optional (B, N) */
   int32_t tile_steps;  /* solver steps staged per shared-memory tile; 0 = auto */
-  int32_t block_envs;  /* environments (threads) per CTA; 0 = auto */
+  int32_t block_envs;  /* reserved (the kernel uses 128 environments per CTA) */
 } ExenvSimArgs;
 /* N+1 = 1 + int(action_stepsize * T / obs_stepsize) (pendulum_env.py:222-225) and the solver-step count of the
  * emulated diffeqsolve loop in the plan dtype. */

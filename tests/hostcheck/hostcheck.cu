@@ -90,10 +90,11 @@ static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, 
     T bw1[7];
     tsit5_dense_weights<T>((T)1, bw1);
     long save_idx = 0;
+    const typename Env::Pre pre = Env::precompute(p);
     const T adv = (T)((dead_d + 0.5) * d->tau), lin_stop = (T)(d->tau * (double)(n_actions - 1));
     for (long n = 0; n < n_steps; ++n) {
       sim_one_step<Env, SOLVER, T>(
-          words[n], (T)dts[n], y, f, have_f, p, aux, bw1, th.data(), save_idx,
+          words[n], (T)dts[n], y, f, have_f, p, pre, aux, bw1, th.data(), save_idx,
           [&](int idx, T *u) {
             const long raw = (long)idx - dead;
             const T *src = actions + (b * n_actions + (raw < 0 ? 0 : raw)) * A;
