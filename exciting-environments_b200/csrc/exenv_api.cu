@@ -10,6 +10,7 @@
 #include <new>
 
 #include "exenv_internal.h"
+#include "exenv_sim_core.cuh"
 
 namespace exenv {
 
@@ -144,31 +145,37 @@ static int build_schedule_t(const ExenvPlan &plan, int64_t n_actions, double obs
     return EXENV_ERR_INVALID;
   }
 
-  // ---- tiles
+  // ---- tiles: at most `tile_steps` solver steps AND at most `tile_steps` saves each (a step with several saves,
+  // e.g. the first one which also saves ts[0], must not push a tile over the staging capacity the fast row
+  // writer is built for)
   out.tile_steps = tile_steps;
   int64_t save_run = 0;
-  for (int64_t n0 = 0; n0 < out.n_steps; n0 += tile_steps) {
+  for (int64_t n0 = 0; n0 < out.n_steps;) {
     SimTile t{};
     t.step_begin = (int)n0;
-    t.step_count = (int)std::min<int64_t>(tile_steps, out.n_steps - n0);
     int64_t lo = INT64_MAX, hi = -1;
-    int sc = 0;
-    for (int n = t.step_begin; n < t.step_begin + t.step_count; ++n) {
+    int sc = 0, cntsteps = 0;
+    for (int64_t n = n0; n < out.n_steps && cntsteps < tile_steps; ++n) {
+      const int add = save_count[(size_t)n];
+      if (cntsteps > 0 && sc + add > tile_steps) break;
       const uint64_t w = out.words[(size_t)n];
       const int64_t base = (int64_t)(w & 0xffffffffull);
       int64_t mx = base;
       for (int s = 0; s < 7; ++s) mx = std::max(mx, base + (int64_t)((w >> (32 + 2 * s)) & 3));
       lo = std::min(lo, base);
       hi = std::max(hi, mx);
-      sc += save_count[(size_t)n];
+      sc += add;
+      ++cntsteps;
     }
+    t.step_count = cntsteps;
     t.save_begin = (int)save_run;
     t.save_cnt = sc;
     if (pmsm && plan.deadtime > 0 && sc > 0) {  // buffer leaves of the saved states index the same staged sequence
       lo = std::min<int64_t>(lo, save_run);
       hi = std::max<int64_t>(hi, save_run + sc - 1);
     }
-    const bool is_last = n0 + tile_steps >= out.n_steps;
+    n0 += cntsteps;
+    const bool is_last = n0 >= out.n_steps;
     if (is_last) hi = std::max<int64_t>(hi, n_actions - 1);  // solver.init at t1 reads the clamped last action
     save_run += sc;
     t.act_lo = (int)lo;
@@ -182,24 +189,31 @@ static int build_schedule_t(const ExenvPlan &plan, int64_t n_actions, double obs
   return EXENV_OK;
 }
 
+template <typename T>
+static int upload_records(const ExenvPlan &plan, SimSchedule &s) {
+  std::vector<SaveRec<T>> recs(std::max<size_t>(1, s.theta.size()));
+  const bool tsit = plan.desc.solver == EXENV_TSIT5;
+  for (size_t i = 0; i < s.theta.size(); ++i) {
+    for (int j = 0; j < 8; ++j) recs[i].v[j] = (T)0;
+    if (tsit)
+      tsit5_dense_weights<T>((T)s.theta[i], recs[i].v);
+    else
+      recs[i].v[0] = (T)s.theta[i];
+  }
+  std::vector<T> dt(s.dt.begin(), s.dt.end());
+  EX_CUDA(cudaMalloc(&s.d_dt, dt.size() * sizeof(T)));
+  EX_CUDA(cudaMalloc(&s.d_theta, recs.size() * sizeof(SaveRec<T>)));
+  EX_CUDA(cudaMemcpy(s.d_dt, dt.data(), dt.size() * sizeof(T), cudaMemcpyHostToDevice));
+  EX_CUDA(cudaMemcpy(s.d_theta, recs.data(), recs.size() * sizeof(SaveRec<T>), cudaMemcpyHostToDevice));
+  return EXENV_OK;
+}
+
 static int upload_schedule(const ExenvPlan &plan, SimSchedule &s) {
-  const bool f64 = plan.desc.dtype == EXENV_F64;
-  const size_t es = f64 ? 8 : 4;
   EX_CUDA(cudaMalloc(&s.d_words, s.words.size() * sizeof(uint64_t)));
-  EX_CUDA(cudaMalloc(&s.d_dt, s.dt.size() * es));
-  EX_CUDA(cudaMalloc(&s.d_theta, std::max<size_t>(1, s.theta.size()) * es));
   EX_CUDA(cudaMalloc(&s.d_tiles, s.tiles.size() * sizeof(SimTile)));
   EX_CUDA(cudaMemcpy(s.d_words, s.words.data(), s.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
   EX_CUDA(cudaMemcpy(s.d_tiles, s.tiles.data(), s.tiles.size() * sizeof(SimTile), cudaMemcpyHostToDevice));
-  if (f64) {
-    EX_CUDA(cudaMemcpy(s.d_dt, s.dt.data(), s.dt.size() * 8, cudaMemcpyHostToDevice));
-    EX_CUDA(cudaMemcpy(s.d_theta, s.theta.data(), s.theta.size() * 8, cudaMemcpyHostToDevice));
-  } else {
-    std::vector<float> a(s.dt.begin(), s.dt.end()), b(s.theta.begin(), s.theta.end());
-    EX_CUDA(cudaMemcpy(s.d_dt, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
-    EX_CUDA(cudaMemcpy(s.d_theta, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
-  }
-  return EXENV_OK;
+  return plan.desc.dtype == EXENV_F64 ? upload_records<double>(plan, s) : upload_records<float>(plan, s);
 }
 
 static void free_schedule(SimSchedule &s) {
@@ -226,7 +240,7 @@ static int auto_tile_steps(const ExenvPlan &plan, int E) {
   const size_t budget = sm_total / ctas - 1024;
   const int cand[] = {64, 48, 32, 24, 16, 12, 8, 4, 2, 1};
   for (int k : cand)
-    if (sim_smem_bytes(plan, E, k + 3, k + 1) <= budget) return k;
+    if (sim_smem_bytes(plan, E, k + 3, k) <= budget) return k;
   return 1;
 }
 

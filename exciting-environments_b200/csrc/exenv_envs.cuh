@@ -61,6 +61,7 @@ struct NoAux {};
 template <typename T>
 struct PmsmAux {
   T omega_el;  // constant over a step / a sim_ahead call (pmsm_env.py:546, 639)
+  int deadtime;
   LutView<T> lut;
 };
 

@@ -35,7 +35,7 @@ struct SimSchedule {
   // device copies
   uint64_t *d_words = nullptr;  // bits 0-31 min action index, 32-45 seven 2-bit stage deltas, 46-49 #saves
   void *d_dt = nullptr;         // T[n_steps]   tnext - tprev
-  void *d_theta = nullptr;      // T[n_save]    dense-output abscissa of every save, in save order
+  void *d_theta = nullptr;      // SaveRec<T>[n_save]  dense-output record of every save, in save order
   SimTile *d_tiles = nullptr;
   // host copies (tests / shape queries)
   std::vector<uint64_t> words;

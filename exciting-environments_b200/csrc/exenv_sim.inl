@@ -8,7 +8,8 @@
 //
 //   prefetch     : the action span of tile t+1 is copied global -> shared with cp.async (LDGSTS, 4/8-byte elements,
 //                  lanes along time = contiguous row segments in HBM, written transposed as [time][env] with an odd
-//                  pitch) while tile t is being integrated: double-buffered, no register staging, no exposed latency
+//                  pitch); it is issued as soon as tile t's integration is finished and lands while tile t's outputs
+//                  are being written: no register staging, no exposed latency
 //   in-place     : each thread de-normalises its own action column (PMSM: dq->alpha/beta, voltage-hexagon clip at
 //                  the advanced angle, dead-time shift -- pmsm_env.py:709-777)
 //   compute      : tile_steps solver steps per thread; every save is the solver's dense output evaluated at the
@@ -54,7 +55,7 @@ struct SimK {
   uint8_t *term;
   const uint64_t *words;
   const T *dts;
-  const T *thetas;
+  const SaveRec<T> *recs;
   const SimTile *tiles;
   int n_tiles, act_cap, save_cap;
   int n_control;
@@ -95,33 +96,31 @@ __device__ __forceinline__ void prefetch_actions(const SimK<T> &a, const SimTile
   constexpr int A = Env::A;
   const int dead = Env::IS_PMSM ? a.deadtime : 0;
   const int k0 = (ti.act_lo < dead) ? (dead - ti.act_lo) : 0;
-  const int n_el = (ti.act_cnt - k0) * A;
+  const int n_el = (ti.act_cnt - k0) * A;  // contiguous scalars per environment row
   const long src_lo = (long)ti.act_lo + k0 - dead;
-  const T *src = a.actions + ((blk0 + warp) * a.n_actions + src_lo) * A;
   const long row_stride = (long)SIM_NW * a.n_actions * A;
-  T *dst = sm_act + (size_t)(k0 * A) * SIM_EP + warp;
-  for (int r = warp; r < rows; r += SIM_NW) {
-    for (int j = lane; j < n_el; j += 32) cp_async_elem<T>(dst + (size_t)j * SIM_EP, src + j);
-    src += row_stride;
-    dst += SIM_NW;
+  for (int j0 = 0; j0 < n_el; j0 += 32) {  // one pass per 32 scalars of the span (1-3 passes)
+    const int j = j0 + lane;
+    const bool on = j < n_el;
+    const T *src = a.actions + ((blk0 + warp) * a.n_actions + src_lo) * A + j;
+    unsigned dst = smem_u32(sm_act + (size_t)(k0 * A + j) * SIM_EP + warp);
+    for (int r = warp; r < rows; r += SIM_NW) {
+      if (on) asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(sizeof(T)) : "memory");
+      src += row_stride;
+      dst += SIM_NW * sizeof(T);
+    }
   }
 }
 
-// Physical-state field `d` of (row r, slot) from the staged values / action tile / inputs.
+// Physical-state field `d` of (row r, slot) from the staged values (PMSM: omega_el is constant per environment).
 template <class Env, typename T>
-__device__ __forceinline__ T staged_field(const SimK<T> &a, const SimTile &ti, const T *sm_act, const T *sm_out,
-                                          long blk0, int d, int r, int slot) {
+__device__ __forceinline__ T staged_field(const SimK<T> &a, const T *sm_out, long blk0, int d, int r, int slot) {
   constexpr int NST = staged_values<Env>();
   if constexpr (Env::IS_PMSM) {
-    if (d == 2) return sm_out[(slot * NST + 0) * SIM_EP + r];
-    if (d == 3) return sm_out[(slot * NST + 1) * SIM_EP + r];
-    if (d == 4) return sm_out[(slot * NST + 2) * SIM_EP + r];
-    if (d == 5) return sm_out[(slot * NST + 3) * SIM_EP + r];
     if (d == 6) return __ldg(a.sin[6] + blk0 + r);
-    // u_dq buffers over time: vstack([buffer]*deadtime, clipped actions); zeros when deadtime == 0
-    if (a.deadtime == 0) return (T)0;
-    const int k = ti.save_begin + slot - ti.act_lo;
-    return sm_act[(k * 2 + d) * SIM_EP + r];
+    // staged order: eps, i_d, i_q, torque, u_d_buffer, u_q_buffer
+    const int v = (d >= 2) ? d - 2 : d + 4;
+    return sm_out[(slot * NST + v) * SIM_EP + r];
   } else {
     return sm_out[(slot * NST + d) * SIM_EP + r];
   }
@@ -132,30 +131,50 @@ __device__ __forceinline__ int pmsm_obs_field(int o) {
   return (o == 0) ? 3 : (o == 1) ? 4 : (o == 2) ? 6 : (o == 3) ? 5 : (o == 6) ? 0 : (o == 7) ? 1 : 2;
 }
 
-// Fast row writer: control_state == [], no epilogue, shared parameters.
+// Fast row writer: control_state == [], no epilogue, shared parameters, at most 32 saves in the tile.
+// A warp-wide store covers 32 consecutive scalars of one environment row when the tile holds more than 16 saves;
+// shorter tiles pack 2 or 4 rows into one store so that lanes stay busy.  A lane keeps a fixed (slot, observation
+// column), so its normalisation constants and smem/global offsets are loop invariants.
 template <class Env, typename T>
 __device__ __forceinline__ void store_tile_fast(const SimK<T> &a, const KParams<T> &kp, const SimTile &ti,
-                                                const T *sm_act, const T *sm_out, long blk0, int rows, int warp,
-                                                int lane) {
-  constexpr int D = Env::D, O = Env::O;
+                                                const T *sm_out, long blk0, int rows, int warp, int lane) {
+  constexpr int D = Env::D, O = Env::O, NST = staged_values<Env>();
   const int cnt = ti.save_cnt;
   const T *pn = kp.v + Env::NSTATIC;
-  // ---- trajectory leaves: one contiguous run of `cnt` samples per (leaf, environment)
+  const int lp = cnt > 16 ? 5 : (cnt > 8 ? 4 : 3);  // log2 of the padded slot count P
+  // ---- trajectory leaves: P slots per row, 32 / P rows per warp-wide store
+  {
+    const int k = lane & ((1 << lp) - 1), rs = lane >> lp, R = 32 >> lp;
+    const bool on = k < cnt;
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    T *leaf = a.traj[d];
-    if (!leaf) continue;
-    T *dst = leaf + (blk0 + warp) * a.n_save + ti.save_begin;
-    const long stride = (long)SIM_NW * a.n_save;
-    for (int r = warp; r < rows; r += SIM_NW) {
-      for (int k = lane; k < cnt; k += 32) dst[k] = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, d, r, k);
-      dst += stride;
+    for (int d = 0; d < D; ++d) {
+      T *leaf = a.traj[d];
+      if (!leaf) continue;
+      if (Env::IS_PMSM && d == 6) {  // omega_el: constant per environment, broadcast over time
+        for (int r = warp * R + rs; r < rows; r += SIM_NW * R)
+          if (on) leaf[(blk0 + r) * a.n_save + ti.save_begin + k] = __ldg(a.sin[6] + blk0 + r);
+        continue;
+      }
+      const int v = Env::IS_PMSM ? ((d >= 2) ? d - 2 : d + 4) : d;
+      const T *src = sm_out + (k * NST + v) * SIM_EP + warp * R + rs;
+      T *dst = leaf + (blk0 + warp * R + rs) * a.n_save + ti.save_begin + k;
+      const long stride = (long)SIM_NW * R * a.n_save;
+      for (int r = warp * R + rs; r < rows; r += SIM_NW * R) {
+        if (on) *dst = *src;
+        src += SIM_NW * R;
+        dst += stride;
+      }
     }
   }
-  // ---- observation rows: cnt * O contiguous scalars; O divides 32, so a lane owns one observation column
+  // ---- observation rows: P * O scalars per row (O divides 32: a lane owns one observation column)
   {
-    constexpr int SPI = 32 / O;  // slots covered by one warp-wide store
-    const int o = lane & (O - 1), ks = lane / O;
+    constexpr int LO = (O == 1) ? 0 : (O == 2) ? 1 : (O == 4) ? 2 : 3;
+    const int lrow = lp + LO;                   // log2 of the padded row length
+    const int llanes = lrow < 5 ? lrow : 5;     // log2 lanes spent on one row
+    const int iters = 1 << (lrow - llanes);     // warp-wide stores per row
+    const int R = 32 >> llanes;                 // rows per warp-wide store
+    const int jl = lane & ((1 << llanes) - 1), rs = lane >> llanes;
+    const int o = lane & (O - 1);
     int fld = o;
     if constexpr (Env::IS_PMSM) fld = pmsm_obs_field(o);
     T mn = pn[0];
@@ -167,21 +186,29 @@ __device__ __forceinline__ void store_tile_fast(const SimK<T> &a, const KParams<
         span = pn[2 * i + 1] - pn[2 * i];
       }
     const InvDiv<T> sdiv = make_invdiv<T>(span);
-    T *dst = a.obs + ((blk0 + warp) * a.n_save + ti.save_begin) * O + lane;
-    const long stride = (long)SIM_NW * a.n_save * O;
-    for (int r = warp; r < rows; r += SIM_NW) {
-      int j = 0;
-      for (int k = ks; k < cnt; k += SPI, j += 32) {
-        const T v = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, fld, r, k);
-        T val;
-        if constexpr (Env::IS_PMSM) {
-          val = (o == 4) ? Mth<T>::cos(v) : (o == 5) ? Mth<T>::sin(v) : norm_inv<true, T>(v, mn, sdiv);
-        } else {
-          val = norm_inv<true, T>(v, mn, sdiv);
+    const int v = Env::IS_PMSM ? ((fld >= 2) ? fld - 2 : fld + 4) : fld;
+    const long stride = (long)SIM_NW * R * a.n_save * O;
+    for (int it = 0; it < iters; ++it) {
+      const int j = it * 32 + jl, k = j >> LO;
+      const bool on = k < cnt;
+      const T *src = sm_out + (k * NST + v) * SIM_EP + warp * R + rs;
+      T *dst = a.obs + ((blk0 + warp * R + rs) * a.n_save + ti.save_begin) * O + j;
+      for (int r = warp * R + rs; r < rows; r += SIM_NW * R) {
+        if (on) {
+          T x;
+          if (Env::IS_PMSM && fld == 6) x = __ldg(a.sin[6] + blk0 + r);
+          else x = *src;
+          T val;
+          if constexpr (Env::IS_PMSM) {
+            val = (o == 4) ? Mth<T>::cos(x) : (o == 5) ? Mth<T>::sin(x) : norm_inv<true, T>(x, mn, sdiv);
+          } else {
+            val = norm_inv<true, T>(x, mn, sdiv);
+          }
+          *dst = val;
         }
-        dst[j] = val;
+        src += SIM_NW * R;
+        dst += stride;
       }
-      dst += stride;
     }
   }
 }
@@ -189,8 +216,7 @@ __device__ __forceinline__ void store_tile_fast(const SimK<T> &a, const KParams<
 // Generic row writer: reference entries, per-environment parameters, fused reward / truncated / terminated.
 template <class Env, typename T, bool PER_ENV>
 __device__ __noinline__ void store_tile_generic(const SimK<T> &a, const KParams<T> &kp, const SimTile &ti,
-                                                const T *sm_act, const T *sm_out, long blk0, int rows, int warp,
-                                                int lane) {
+                                                const T *sm_out, long blk0, int rows, int warp, int lane) {
   constexpr int D = Env::D, O = Env::O, NP = num_params<Env>();
   const int cnt = ti.save_cnt;
   const int OW = O + a.n_control;
@@ -210,7 +236,7 @@ __device__ __noinline__ void store_tile_generic(const SimK<T> &a, const KParams<
     for (int d = 0; d < D; ++d) {
       T *dst = a.traj[d];
       if (dst)
-        for (int k = lane; k < cnt; k += 32) dst[row0 + k] = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, d, r, k);
+        for (int k = lane; k < cnt; k += 32) dst[row0 + k] = staged_field<Env, T>(a, sm_out, blk0, d, r, k);
     }
     {
       T *dst = a.obs + row0 * OW;
@@ -221,7 +247,7 @@ __device__ __noinline__ void store_tile_generic(const SimK<T> &a, const KParams<
         if (o < O) {
           int fld = o;
           if constexpr (Env::IS_PMSM) fld = pmsm_obs_field(o);
-          const T fv = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, fld, r, k);
+          const T fv = staged_field<Env, T>(a, sm_out, blk0, fld, r, k);
           T mn = pn[0], mx = pn[1];
 #pragma unroll
           for (int i = 1; i < D; ++i)
@@ -253,7 +279,7 @@ __device__ __noinline__ void store_tile_generic(const SimK<T> &a, const KParams<
         T sv[D], rf[D], ob[O + EXENV_MAX_CONTROL];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          sv[d] = staged_field<Env, T>(a, ti, sm_act, sm_out, blk0, d, r, k);
+          sv[d] = staged_field<Env, T>(a, sm_out, blk0, d, r, k);
           rf[d] = (a.n_control > 0) ? __ldg(a.ref[d] + br) : (T)0;
         }
         observe<Env, T>(sv, pr, ob);
@@ -292,17 +318,17 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
   const int rows = (int)((a.B - blk0) < (long)SIM_E ? (a.B - blk0) : (long)SIM_E);  // valid environments here
 
   const size_t act_elems = (size_t)a.act_cap * A * SIM_EP;
-  T *sm_act0 = reinterpret_cast<T *>(smem_raw);  // two [act_cap * A][EP] buffers
-  T *sm_out = sm_act0 + 2 * act_elems;           // [save_cap * NST][EP]
+  T *sm_act = reinterpret_cast<T *>(smem_raw);  // [act_cap * A][EP]
+  T *sm_out = sm_act + act_elems;               // [save_cap * NST][EP]
 
   // first tile's actions are on their way while the constants below are set up
-  prefetch_actions<Env, T>(a, a.tiles[0], sm_act0, blk0, rows, warp, lane);
+  prefetch_actions<Env, T>(a, a.tiles[0], sm_act, blk0, rows, warp, lane);
   cp_async_commit();
 
   typename Env::Aux aux{};
   if constexpr (Env::IS_PMSM && Env::SATURATED) {
     // stage the flux maps once per CTA: TMA bulk copy + mbarrier
-    size_t off = ((2 * act_elems + (size_t)a.save_cap * NST * SIM_EP) * sizeof(T) + 15) & ~(size_t)15;
+    size_t off = ((act_elems + (size_t)a.save_cap * NST * SIM_EP) * sizeof(T) + 15) & ~(size_t)15;
     unsigned char *sm_lut = smem_raw + off;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut_bytes);
     if (e == 0) {
@@ -349,6 +375,7 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
     y[1] = s0[4];
     y[2] = s0[2];
     aux.omega_el = s0[6];
+    aux.deadtime = a.deadtime;
   } else {
 #pragma unroll
     for (int i = 0; i < NODE; ++i) y[i] = s0[i];
@@ -359,23 +386,13 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
   T last[NST];
 #pragma unroll
   for (int i = 0; i < NST; ++i) last[i] = (T)0;
-  // dense-output weights at theta == 1 (the common save position), evaluated like any other theta
-  T bw1[7];
-  if constexpr (SOLVER == EXENV_TSIT5) tsit5_dense_weights<T>((T)1, bw1);
-
   long save_idx = 0;
   const bool fast_store = !PER_ENV && a.n_control == 0 && !(a.reward || a.trunc || a.term);
 
   for (int tile = 0; tile < a.n_tiles; ++tile) {
     const SimTile ti = a.tiles[tile];
-    T *sm_act = sm_act0 + (size_t)(tile & 1) * act_elems;
     cp_async_wait_all();
-    __syncthreads();  // this tile's actions have landed; the previous store phase is done with sm_out / the other buffer
-    if (tile + 1 < a.n_tiles) {
-      prefetch_actions<Env, T>(a, a.tiles[tile + 1], sm_act0 + (size_t)((tile + 1) & 1) * act_elems, blk0, rows, warp,
-                               lane);
-      cp_async_commit();
-    }
+    __syncthreads();  // this tile's actions have landed; the previous store phase is done with sm_out
 
     if (valid) {
       T *col = sm_act + e;  // this environment's column of the [time][env] tile
@@ -394,17 +411,23 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
       const T *col0 = col - (long)ti.act_lo * A * SIM_EP;  // indexable by absolute ZOH index
       T *out_col = sm_out + e - (long)ti.save_begin * NST * SIM_EP;
       const int n_end = ti.step_begin + ti.step_count;
+      // the schedule (word, dt, first save record) of step n+1 is fetched while step n is integrated
       uint64_t w_next = __ldg(a.words + ti.step_begin);
       T dt_next = __ldg(a.dts + ti.step_begin);
+      SaveRec<T> rec_next = a.recs[save_idx];
       for (int n = ti.step_begin; n < n_end; ++n) {
         const uint64_t w = w_next;
         const T dt = dt_next;
+        const SaveRec<T> rec = rec_next;
         if (n + 1 < n_end) {
           w_next = __ldg(a.words + n + 1);
           dt_next = __ldg(a.dts + n + 1);
+          long nxt = save_idx + sched_saves(w);
+          if (nxt > a.n_save - 1) nxt = a.n_save - 1;
+          rec_next = a.recs[nxt];
         }
         sim_one_step<Env, SOLVER, T>(
-            w, dt, y, f, have_f, p, pre, aux, bw1, a.thetas, save_idx,
+            w, dt, y, f, have_f, p, pre, aux, rec, a.recs, save_idx,
             [&](int idx, T *u) {
 #pragma unroll
               for (int c = 0; c < A; ++c) u[c] = col0[(idx * A + c) * SIM_EP];
@@ -421,17 +444,24 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
     } else {
       save_idx += ti.save_cnt;
     }
-    __syncthreads();
+    __syncthreads();  // integration of this tile is finished: sm_out is complete, sm_act is free again
+
+    // the next tile's actions travel while this tile's outputs are written
+    const bool more = tile + 1 < a.n_tiles;
+    if (more) {
+      prefetch_actions<Env, T>(a, a.tiles[tile + 1], sm_act, blk0, rows, warp, lane);
+      cp_async_commit();
+    }
 
     // ---- store phase: rows of the batch-major outputs, lanes along time ---------------------------------------
     if (ti.save_cnt > 0) {
       if constexpr (!PER_ENV) {
-        if (fast_store)
-          store_tile_fast<Env, T>(a, kp, ti, sm_act, sm_out, blk0, rows, warp, lane);
+        if (fast_store && ti.save_cnt <= 32)
+          store_tile_fast<Env, T>(a, kp, ti, sm_out, blk0, rows, warp, lane);
         else
-          store_tile_generic<Env, T, false>(a, kp, ti, sm_act, sm_out, blk0, rows, warp, lane);
+          store_tile_generic<Env, T, false>(a, kp, ti, sm_out, blk0, rows, warp, lane);
       } else {
-        store_tile_generic<Env, T, true>(a, kp, ti, sm_act, sm_out, blk0, rows, warp, lane);
+        store_tile_generic<Env, T, true>(a, kp, ti, sm_out, blk0, rows, warp, lane);
       }
     }
   }
@@ -439,15 +469,10 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
   // ---- last_state (core_env.py:484-488) and the fresh solver.init derivative at (t1, y_last) --------------------
   if (valid) {
     const SimTile tl = a.tiles[a.n_tiles - 1];
-    const T *sm_act = sm_act0 + (size_t)((a.n_tiles - 1) & 1) * act_elems;
     T sl[D];
     if constexpr (Env::IS_PMSM) {
-      sl[0] = sl[1] = (T)0;
-      if (a.deadtime > 0) {
-        const int k = (int)(a.n_save - 1 - tl.act_lo);  // buffer leaf of the last saved state
-        sl[0] = sm_act[(k * 2) * SIM_EP + e];
-        sl[1] = sm_act[(k * 2 + 1) * SIM_EP + e];
-      }
+      sl[0] = last[4];
+      sl[1] = last[5];
       sl[2] = last[0];
       sl[3] = last[1];
       sl[4] = last[2];
@@ -485,7 +510,7 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
 template <class Env, typename T>
 static size_t smem_bytes_t(const ExenvPlan &plan, int act_cap, int save_cap) {
   constexpr int NST = staged_values<Env>();
-  size_t n = (size_t)(2 * act_cap * Env::A + save_cap * NST) * SIM_EP * sizeof(T);
+  size_t n = (size_t)(act_cap * Env::A + save_cap * NST) * SIM_EP * sizeof(T);
   if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) {
     n = (n + 15) & ~(size_t)15;
     n += plan.lut.bytes + 16;
@@ -513,7 +538,7 @@ static int launch_sim_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimS
   a.term = x.terminated;
   a.words = sch.d_words;
   a.dts = (const T *)sch.d_dt;
-  a.thetas = (const T *)sch.d_theta;
+  a.recs = (const SaveRec<T> *)sch.d_theta;
   a.tiles = sch.d_tiles;
   a.n_tiles = sch.n_tiles;
   a.act_cap = sch.act_cap;

@@ -17,11 +17,19 @@ EX_HD int sched_delta(uint64_t w, int stage) { return (int)((w >> (32 + 2 * stag
 EX_HD int sched_saves(uint64_t w) { return (int)((w >> 46) & 15ull); }
 EX_HD int sched_dmax(uint64_t w) { return (int)((w >> 50) & 3ull); }  // largest stage offset of the step
 
-// Number of values staged per save: the post-processed ODE state (+ torque for PMSM: eps, i_d, i_q, torque).
+// Number of values staged per save: the post-processed ODE state; PMSM: eps, i_d, i_q, torque, u_d_buffer,
+// u_q_buffer.
 template <class Env>
 constexpr int staged_values() {
-  return Env::IS_PMSM ? 4 : Env::NODE;
+  return Env::IS_PMSM ? 6 : Env::NODE;
 }
+
+// Per-save dense-output record built by the host (exenv_api.cu): Tsit5 -> the seven weights b_i(theta) of
+// diffrax's _Tsit5Interpolation, evaluated in T exactly like tsit5_dense_weights; Euler -> v[0] = theta.
+template <typename T>
+struct alignas(16) SaveRec {
+  T v[8];
+};
 
 // Physical action for index `q` of the zero-order-hold sequence the solver sees.
 //  generic envs : denormalize_action of raw action q                               (core_env.py:468)
@@ -55,13 +63,14 @@ EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, int dea
 //   y[NODE]      ODE state, updated in place
 //   f[NODE]      Tsit5 FSAL derivative carried between steps (have_f tells whether it is valid)
 //   fetch(idx,u) physical action of ZOH index idx (absolute); called once per distinct index of the step
-//   sink(save_index, staged[NST]) receives every saved sample, already wrapped / clipped (+ torque)
-//   thetas       dense-output abscissae, consumed in order starting at save_idx
+//   sink(save_index, staged[NST]) receives every saved sample, already wrapped / clipped (+ torque, PMSM buffers)
+//   rec0 / recs  per-save dense-output records: rec0 = recs[save_idx] (prefetched by the caller one step ahead so its
+//                latency is off the critical path), further saves of the same step read recs[] directly
 // Divisions by parameter-only denominators use the prepared reciprocals (div_inv<true>), see exenv_math.cuh.
 template <class Env, int SOLVER, typename T, class Fetch, class Sink>
 EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, const typename Env::Pre &pre,
-                        typename Env::Aux &aux, const T *bw1, const T *thetas, long &save_idx, Fetch &&fetch,
-                        Sink &&sink) {
+                        typename Env::Aux &aux, const SaveRec<T> &rec0, const SaveRec<T> *recs, long &save_idx,
+                        Fetch &&fetch, Sink &&sink) {
   constexpr int NODE = Env::NODE, A = Env::A, NST = staged_values<Env>();
   const int base = sched_base(w);
   T y1[NODE], k[7][NODE];
@@ -114,24 +123,18 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, 
   // SaveAt(ts): dense output (LocalLinearInterpolation / _Tsit5Interpolation) at the scheduled abscissae
   const int ns = sched_saves(w);
   for (int q = 0; q < ns; ++q) {
-    const T th = thetas[save_idx];
+    SaveRec<T> rec = rec0;
+    if (q > 0) rec = recs[save_idx];
     T ysv[NODE];
     if constexpr (SOLVER == EXENV_EULER) {
 #pragma unroll
-      for (int i = 0; i < NODE; ++i) ysv[i] = y[i] + th * (y1[i] - y[i]);
+      for (int i = 0; i < NODE; ++i) ysv[i] = y[i] + rec.v[0] * (y1[i] - y[i]);
     } else {
-      T bw[7];
-      if (th == (T)1) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) bw[j] = bw1[j];
-      } else {
-        tsit5_dense_weights<T>(th, bw);
-      }
 #pragma unroll
       for (int i = 0; i < NODE; ++i) {
-        T acc = bw[0] * k[0][i];
+        T acc = rec.v[0] * k[0][i];
 #pragma unroll
-        for (int j = 1; j < 7; ++j) acc += bw[j] * k[j][i];
+        for (int j = 1; j < 7; ++j) acc += rec.v[j] * k[j][i];
         ysv[i] = y[i] + acc;
       }
     }
@@ -142,6 +145,13 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, 
       st[1] = ysv[0];
       st[2] = ysv[1];
       st[3] = Env::torque(ysv[0], ysv[1], p, aux);
+      // u_dq buffer leaves of saved state j: vstack([buffer]*deadtime, clipped actions)[j]; zeros when
+      // deadtime == 0 (pmsm_env.py:785-791) -- the same dead-time shifted sequence the solver reads
+      T ub[A];
+      ub[0] = ub[1] = (T)0;
+      if (aux.deadtime > 0) fetch((int)save_idx, ub);
+      st[4] = ub[0];
+      st[5] = ub[1];
     } else {
 #pragma unroll
       for (int i = 0; i < NODE; ++i) st[i] = ysv[i];

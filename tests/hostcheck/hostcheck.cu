@@ -66,7 +66,12 @@ static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, 
                   const uint64_t *words, const double *dts, const double *thetas, const T *const *sin,
                   const T *actions, T *const *traj /* NST leaves (B, n_save) */) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, NST = staged_values<Env>();
-  std::vector<T> th(thetas, thetas + n_save);
+  std::vector<SaveRec<T>> recs((size_t)n_save);
+  for (long i = 0; i < n_save; ++i) {
+    for (int j = 0; j < 8; ++j) recs[(size_t)i].v[j] = (T)0;
+    if (SOLVER == EXENV_EULER) recs[(size_t)i].v[0] = (T)thetas[i];
+    else tsit5_dense_weights<T>((T)thetas[i], recs[(size_t)i].v);
+  }
   const double dead_d = Env::IS_PMSM ? d->p[6] : 0.0;
   const int dead = (int)dead_d;
   for (long b = 0; b < B; ++b) {
@@ -79,6 +84,7 @@ static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, 
     if constexpr (Env::IS_PMSM) {
       aux.lut = view<T>(lut);
       aux.omega_el = s0[6];
+      aux.deadtime = dead;
       y[0] = s0[3];
       y[1] = s0[4];
       y[2] = s0[2];
@@ -87,14 +93,13 @@ static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, 
     }
     for (int i = 0; i < NODE; ++i) f[i] = 0;
     bool have_f = false;
-    T bw1[7];
-    tsit5_dense_weights<T>((T)1, bw1);
     long save_idx = 0;
     const typename Env::Pre pre = Env::precompute(p);
     const T adv = (T)((dead_d + 0.5) * d->tau), lin_stop = (T)(d->tau * (double)(n_actions - 1));
     for (long n = 0; n < n_steps; ++n) {
       sim_one_step<Env, SOLVER, T>(
-          words[n], (T)dts[n], y, f, have_f, p, pre, aux, bw1, th.data(), save_idx,
+          words[n], (T)dts[n], y, f, have_f, p, pre, aux, recs[(size_t)(save_idx < n_save ? save_idx : n_save - 1)],
+          recs.data(), save_idx,
           [&](int idx, T *u) {
             const long raw = (long)idx - dead;
             const T *src = actions + (b * n_actions + (raw < 0 ? 0 : raw)) * A;

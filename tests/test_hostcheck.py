@@ -72,7 +72,7 @@ def hc_sim(lib, orc, state, actions, obs_dt, act_dt, tile_steps=32):
     lut, keep = hc_lut(orc)
     B, T = actions.shape[0], actions.shape[1]
     info, words, dt, theta, tiles = ex._lib.schedule(d, T, obs_dt, act_dt, tile_steps)
-    nst = 4 if orc.env == "pmsm" else orc.node
+    nst = 6 if orc.env == "pmsm" else orc.node
     traj = [np.zeros((B, info.n_save), orc.dtype) for _ in range(nst)]
     actions = np.ascontiguousarray(actions, orc.dtype)
     lib.hc_sim(C.byref(d), C.byref(lut) if lut else None, C.c_long(B), C.c_long(T), C.c_long(info.n_save),
@@ -109,7 +109,8 @@ def test_schedule_and_sim_core_match_oracle(hostcheck_lib, env, obs_dt, act_dt, 
     assert info.n_steps == ref["n_steps"]
     assert info.n_save == ref["obs"].shape[1]
     if orc.env == "pmsm":
-        pairs = [(traj[0], ref["traj"][2]), (traj[1], ref["traj"][3]), (traj[2], ref["traj"][4]), (traj[3], ref["traj"][5])]
+        pairs = [(traj[0], ref["traj"][2]), (traj[1], ref["traj"][3]), (traj[2], ref["traj"][4]),
+                 (traj[3], ref["traj"][5]), (traj[4], ref["traj"][0]), (traj[5], ref["traj"][1])]
     else:
         pairs = list(zip(traj, ref["traj"]))
     # chaotic envs amplify rounding differences along the horizon; tolerances are per-trajectory here, the per-step
