@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched dynamics hot path on N B200s (driver contract in the task statement).
+
+Workload (BASELINE.json configs[1]): MASS_SPRING_DAMPER, batch 2^20 environments PER GPU (weak scaling: the batch
+axis shards with no collective), diffrax-Tsit5 `vmap_sim_ahead` over 2000 steps (obs_stepsize = action_stepsize =
+tau = 1e-4), float32, synthetic uniform(-1, 1) states/actions.  One bench "step" = one sim_ahead pass over the batch
+= B * 2000 env-steps, one launch of the persistent sm_100a kernel.
+
+  value      env-steps/s with inputs and outputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e        the same call through the C ABI's host-buffer entry point (exenv_sim_ahead_host): pinned host inputs are
+             copied H2D, outputs D2H, inside the timed region
+  roofline   algorithmic HBM bytes (S*(A+O+D) = 20 B per env-step) / measured launch time vs the measured copy peak
+  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, OpenMP over all host cores) --
+             JAX/diffrax are not installable in this image, so the reference's own jit(vmap) cannot be timed.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ENV, SOLVER, T_STEPS, TAU = "mass_spring_damper", "Tsit5", 2000, 1e-4
+B_PER_GPU = 1 << 20
+S, A, O, D = 4, 1, 2, 2
+BYTES_PER_ENV_STEP = S * (A + O + D)  # actions in, observations + D trajectory leaves out
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=B_PER_GPU, help="environments per GPU (default: the BASELINE config)")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def config_dict(args, batch):
+    return {"workload": f"{ENV} batch={batch}/GPU Tsit5 vmap_sim_ahead {T_STEPS} steps tau={TAU} float32 "
+                        f"(BASELINE.json configs[1])",
+            "env": ENV, "solver": SOLVER, "batch_per_gpu": batch, "n_steps": T_STEPS, "tau": TAU,
+            "l2_policy": "inputs (8.4 GB actions) and outputs (33.6 GB) are far larger than the 126 MB L2",
+            "parallelism": f"batch-sharded x{args.gpus}, no collective"}
+
+
+# ---- CPU arm: the restated reference path on the host cores ------------------------------------------------------------
+def cpu_sample(batch, n_threads):
+    """One pass of the oracle over `batch` environments; returns seconds."""
+    import numpy as np
+
+    from oracle import oracle as Or
+
+    os.environ["OMP_NUM_THREADS"] = str(n_threads)
+    orc = Or.Oracle(ENV, solver=Or.TSIT5, dtype=np.float32, tau=TAU)
+    rng = np.random.default_rng(1234)
+    state = [rng.uniform(-5, 5, batch).astype(np.float32) for _ in range(2)]
+    actions = rng.uniform(-1, 1, (batch, T_STEPS, 1)).astype(np.float32)
+    t0 = time.perf_counter()
+    orc.sim_ahead(state, actions, TAU, TAU)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(target_seconds=12.0):
+    cores = os.cpu_count() or 1
+    probe_b = 1 << 10
+    t = cpu_sample(probe_b, cores)
+    rate = probe_b * T_STEPS / t
+    batch = int(min(1 << 20, max(probe_b, 2 ** int(__import__("math").log2(max(1.0, rate * target_seconds / T_STEPS))))))
+    t = cpu_sample(batch, cores)
+    return {"value": batch * T_STEPS / t, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/exenv_oracle.c (C restatement of the reference path, OpenMP) on {batch} envs x "
+                      f"{T_STEPS} Tsit5 steps, float32, {t:.2f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    probe = cpu_sample(1 << 10, cores)
+    rate = (1 << 10) * T_STEPS / probe
+    batch = 1 << max(10, min(17, int(__import__("math").log2(max(1.0, rate * 4.0 / T_STEPS)))))
+    for _ in range(args.warmup):
+        cpu_sample(min(batch, 1 << 12), cores)
+    times = [cpu_sample(batch, cores) for _ in range(args.steps)]
+    tot = sum(times)
+    value = batch * T_STEPS * args.steps / tot
+    line = {"impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, args.batch),
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"each step = oracle C restatement (OpenMP, {cores} threads) over {batch} envs "
+                                       f"x {T_STEPS} Tsit5 steps; the reference's JAX jit(vmap) path is not "
+                                       f"installable here (no jax/diffrax wheels, no network)"},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm = sorted(float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        if sm:
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = max(float(r[1]) for r in rows if len(r) >= 7)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in rows)]
+            out["samples"] = len(sm)
+        return out
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch(batch):
+    """dram bytes of the dominant kernel from the committed `ncu --set full` summary, scaled to this launch."""
+    p = ROOT / "profiles" / "sim_kernel_traffic.json"
+    if p.exists():
+        try:
+            d = json.load(open(p))
+            return d["dram_bytes_per_env_step"] * batch * T_STEPS
+        except Exception:
+            pass
+    return None
+
+
+def run_b200(args):
+    import torch
+
+    import exciting_environments_b200 as ex
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    env = ex.MassSpringDamper(batch_size=B, solver=ex.Tsit5(), tau=TAU, dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + 1000 * 2 + rank)
+    _, state = env.vmap_reset(rng=gen)
+    actions = torch.rand((B, T_STEPS, A), device=dev, generator=gen) * 2 - 1
+    out = dict(obs=torch.empty((B, T_STEPS + 1, O), device=dev),
+               traj=[torch.empty((B, T_STEPS + 1), device=dev) for _ in range(D)])
+
+    def step():
+        return env._sim_impl(env.env_properties, B, state, actions, TAU, TAU, out=out)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ex.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = ex.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_max = float(t.item())
+    value = world * B * T_STEPS * args.steps / elapsed_max
+
+    # ---- end to end through the C ABI with host buffers (rank-local, then max over ranks)
+    e2e = None
+    if not args.no_e2e:
+        L = ex._lib
+        NS = T_STEPS + 1
+        try:
+            h_state = [getattr(state.physical_state, n).cpu().pin_memory() for n in env.PHYS_FIELDS]
+            h_act = actions.cpu().pin_memory()
+            h_obs = torch.empty((B, NS, O), dtype=torch.float32).pin_memory()
+            h_traj = [torch.empty((B, NS), dtype=torch.float32).pin_memory() for _ in range(D)]
+            h_last = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(D)]
+            a = L.ExenvSimArgs()
+            a.batch, a.n_actions, a.obs_stepsize, a.action_stepsize, a.max_steps = B, T_STEPS, TAU, TAU, 4096
+            for i in range(D):
+                a.state_in[i], a.traj[i], a.last[i] = h_state[i].data_ptr(), h_traj[i].data_ptr(), h_last[i].data_ptr()
+            a.actions, a.obs = h_act.data_ptr(), h_obs.data_ptr()
+            plan = env._plan().handle
+            n_e2e = max(1, min(args.steps, 3))
+            L.check(L.lib().exenv_sim_ahead_host(plan, C.byref(a), 0))  # warm-up (allocations, first touch)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                L.check(L.lib().exenv_sim_ahead_host(plan, C.byref(a), 0))
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            h2d = h_act.numel() * 4 + sum(x.numel() for x in h_state) * 4
+            d2h = h_obs.numel() * 4 + sum(x.numel() for x in h_traj) * 4 + sum(x.numel() for x in h_last) * 4
+            ok = bool(torch.equal(h_obs[:64], out["obs"][:64].cpu()))
+            e2e = {"value": world * B * T_STEPS * n_e2e / float(tt.item()), "unit": "env-steps/s",
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                   "matches_device_path": ok,
+                   "how": "exenv_sim_ahead_host: pinned host buffers, chunked H2D / kernel / D2H on 3 streams, "
+                          "wall clock around the blocking C call (max over ranks)"}
+            del h_obs, h_traj, h_act
+        except Exception as exc:  # e.g. not enough host memory to pin 42 GB
+            e2e = {"value": None, "unit": "env-steps/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                   "error": str(exc)[:200]}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        launch_s = elapsed / args.steps  # one launch per step on this rank
+        achieved = BYTES_PER_ENV_STEP * B * T_STEPS / launch_s / 1e9
+        line = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_max / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_dict(args, B), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": ncu_traffic_per_launch(B), "peak_source": peak_src,
+                             "kernel": "exenv::sim_kernel<MassSpringDamper<float>, Tsit5, float>",
+                             "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP}}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as exc:
+                line["cpu_baseline"] = {"value": None, "error": str(exc)[:200]}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
