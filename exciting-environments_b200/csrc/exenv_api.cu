@@ -191,7 +191,8 @@ static int build_schedule_t(const ExenvPlan &plan, int64_t n_actions, double obs
 
 template <typename T>
 static int upload_records(const ExenvPlan &plan, SimSchedule &s) {
-  std::vector<SaveRec<T>> recs(std::max<size_t>(1, s.theta.size()));
+  std::vector<SaveRec<T>> recs(s.theta.size() + 1);  // + one look-ahead entry
+  for (int j = 0; j < 8; ++j) recs.back().v[j] = (T)0;
   const bool tsit = plan.desc.solver == EXENV_TSIT5;
   for (size_t i = 0; i < s.theta.size(); ++i) {
     for (int j = 0; j < 8; ++j) recs[i].v[j] = (T)0;
@@ -201,6 +202,7 @@ static int upload_records(const ExenvPlan &plan, SimSchedule &s) {
       recs[i].v[0] = (T)s.theta[i];
   }
   std::vector<T> dt(s.dt.begin(), s.dt.end());
+  dt.push_back((T)0);  // look-ahead padding (the kernel fetches step n+1 while integrating step n)
   EX_CUDA(cudaMalloc(&s.d_dt, dt.size() * sizeof(T)));
   EX_CUDA(cudaMalloc(&s.d_theta, recs.size() * sizeof(SaveRec<T>)));
   EX_CUDA(cudaMemcpy(s.d_dt, dt.data(), dt.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -209,9 +211,11 @@ static int upload_records(const ExenvPlan &plan, SimSchedule &s) {
 }
 
 static int upload_schedule(const ExenvPlan &plan, SimSchedule &s) {
-  EX_CUDA(cudaMalloc(&s.d_words, s.words.size() * sizeof(uint64_t)));
+  std::vector<uint64_t> words(s.words);
+  words.push_back(0);  // look-ahead padding
+  EX_CUDA(cudaMalloc(&s.d_words, words.size() * sizeof(uint64_t)));
   EX_CUDA(cudaMalloc(&s.d_tiles, s.tiles.size() * sizeof(SimTile)));
-  EX_CUDA(cudaMemcpy(s.d_words, s.words.data(), s.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  EX_CUDA(cudaMemcpy(s.d_words, words.data(), words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
   EX_CUDA(cudaMemcpy(s.d_tiles, s.tiles.data(), s.tiles.size() * sizeof(SimTile), cudaMemcpyHostToDevice));
   return plan.desc.dtype == EXENV_F64 ? upload_records<double>(plan, s) : upload_records<float>(plan, s);
 }
@@ -240,7 +244,7 @@ static int auto_tile_steps(const ExenvPlan &plan, int E) {
   const size_t budget = sm_total / ctas - 1024;
   const int cand[] = {64, 48, 32, 24, 16, 12, 8, 4, 2, 1};
   for (int k : cand)
-    if (sim_smem_bytes(plan, E, k + 3, k) <= budget) return k;
+    if (sim_smem_bytes(plan, k, k + 3, k) <= budget) return k;
   return 1;
 }
 
@@ -559,7 +563,7 @@ static int prepare_sim(ExenvPlan *plan, const ExenvSimArgs *a, int *E_out, SimSc
               (long long)s.n_steps, (long long)max_steps);
     return EXENV_ERR_MAX_STEPS;
   }
-  const size_t smem = sim_smem_bytes(*plan, E, s.act_cap, s.save_cap);
+  const size_t smem = sim_smem_bytes(*plan, s.tile_steps, s.act_cap, s.save_cap);
   if (smem > 227 * 1024) {
     set_error("sim_ahead tile (%d steps x %d envs) needs %zu bytes of shared memory (> 227 KB)", K, E, smem);
     return EXENV_ERR_INVALID;

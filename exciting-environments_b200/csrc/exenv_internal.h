@@ -73,8 +73,8 @@ int launch_reset_f32(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_
 int launch_reset_f64(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream);
 int launch_sim_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_sim_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
-size_t sim_smem_bytes_f32(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap);
-size_t sim_smem_bytes_f64(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap);
+size_t sim_smem_bytes_f32(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);
+size_t sim_smem_bytes_f64(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);
 
 inline int launch_step(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t s) {
   return plan.desc.dtype == EXENV_F64 ? launch_step_f64(plan, a, s) : launch_step_f32(plan, a, s);
@@ -85,10 +85,10 @@ inline int launch_reset(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStre
 inline int launch_sim(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t s) {
   return plan.desc.dtype == EXENV_F64 ? launch_sim_f64(plan, a, sch, s) : launch_sim_f32(plan, a, sch, s);
 }
-// Shared-memory bytes the sim kernel needs for (block_envs, act_cap, save_cap); used to size tiles.
-inline size_t sim_smem_bytes(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap) {
-  return plan.desc.dtype == EXENV_F64 ? sim_smem_bytes_f64(plan, block_envs, act_cap, save_cap)
-                                      : sim_smem_bytes_f32(plan, block_envs, act_cap, save_cap);
+// Shared-memory bytes the sim kernel needs for tiles of (step_cap steps, act_cap actions, save_cap saves).
+inline size_t sim_smem_bytes(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap) {
+  return plan.desc.dtype == EXENV_F64 ? sim_smem_bytes_f64(plan, step_cap, act_cap, save_cap)
+                                      : sim_smem_bytes_f32(plan, step_cap, act_cap, save_cap);
 }
 int sim_block_envs(int64_t batch, int requested);
 

@@ -57,7 +57,7 @@ struct SimK {
   const T *dts;
   const SaveRec<T> *recs;
   const SimTile *tiles;
-  int n_tiles, act_cap, save_cap;
+  int n_tiles, act_cap, save_cap, step_cap;
   int n_control;
   int control[EXENV_MAX_CONTROL];
   int deadtime;
@@ -67,6 +67,13 @@ struct SimK {
   int lut_nx, lut_ny;
   T lut_inv_dx, lut_inv_dy;
 };
+
+// bytes of the per-tile schedule slice in shared memory (records, words, step lengths), 16-byte aligned
+template <typename T>
+__host__ __device__ constexpr size_t sim_sched_bytes(int step_cap, int save_cap) {
+  return ((size_t)(save_cap + 1) * sizeof(SaveRec<T>) + (size_t)(step_cap + 2) * 8 + (size_t)(step_cap + 2) * sizeof(T) + 15) &
+         ~(size_t)15;
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -110,6 +117,31 @@ __device__ __forceinline__ void prefetch_actions(const SimK<T> &a, const SimTile
       dst += SIM_NW * sizeof(T);
     }
   }
+}
+
+// The tile's slice of the host-built schedule (step words, step lengths, dense-output records; each with one
+// look-ahead entry) is copied next to the actions, so the step loop only touches shared memory.
+template <typename T>
+struct SchedSmem {
+  uint64_t *words;
+  T *dts;
+  SaveRec<T> *recs;
+};
+template <typename T>
+__device__ __forceinline__ void prefetch_schedule(const SimK<T> &a, const SimTile &ti, const SchedSmem<T> &sm, int e) {
+  for (int i = e; i <= ti.step_count; i += SIM_E) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sm.words + i)),
+                 "l"(a.words + ti.step_begin + i)
+                 : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(sm.dts + i)),
+                 "l"(a.dts + ti.step_begin + i), "n"(sizeof(T))
+                 : "memory");
+  }
+  constexpr int CH = sizeof(SaveRec<T>) / 16;  // 16-byte chunks per record
+  const char *src = reinterpret_cast<const char *>(a.recs + ti.save_begin);
+  char *dst = reinterpret_cast<char *>(sm.recs);
+  for (int i = e; i < (ti.save_cnt + 1) * CH; i += SIM_E)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 16 * i)), "l"(src + 16 * i) : "memory");
 }
 
 // Physical-state field `d` of (row r, slot) from the staged values (PMSM: omega_el is constant per environment).
@@ -306,7 +338,8 @@ __device__ __noinline__ void store_tile_generic(const SimK<T> &a, const KParams<
 }
 
 template <class Env, int SOLVER, typename T, bool PER_ENV>
-__global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KParams<T> kp) {
+__global__ void __launch_bounds__(SIM_E)
+    sim_kernel(const __grid_constant__ SimK<T> a, const __grid_constant__ KParams<T> kp) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, NP = num_params<Env>();
   constexpr int NST = staged_values<Env>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -318,17 +351,22 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
   const int rows = (int)((a.B - blk0) < (long)SIM_E ? (a.B - blk0) : (long)SIM_E);  // valid environments here
 
   const size_t act_elems = (size_t)a.act_cap * A * SIM_EP;
-  T *sm_act = reinterpret_cast<T *>(smem_raw);  // [act_cap * A][EP]
-  T *sm_out = sm_act + act_elems;               // [save_cap * NST][EP]
+  SchedSmem<T> sched;
+  sched.recs = reinterpret_cast<SaveRec<T> *>(smem_raw);                                    // [save_cap + 1]
+  sched.words = reinterpret_cast<uint64_t *>(sched.recs + (a.save_cap + 1));               // [step_cap + 1]
+  sched.dts = reinterpret_cast<T *>(sched.words + (a.step_cap + 2));                        // [step_cap + 1]
+  T *sm_act = reinterpret_cast<T *>(smem_raw + sim_sched_bytes<T>(a.step_cap, a.save_cap));  // [act_cap * A][EP]
+  T *sm_out = sm_act + act_elems;                                                           // [save_cap * NST][EP]
 
-  // first tile's actions are on their way while the constants below are set up
+  // first tile's actions and schedule are on their way while the constants below are set up
   prefetch_actions<Env, T>(a, a.tiles[0], sm_act, blk0, rows, warp, lane);
+  prefetch_schedule<T>(a, a.tiles[0], sched, e);
   cp_async_commit();
 
   typename Env::Aux aux{};
   if constexpr (Env::IS_PMSM && Env::SATURATED) {
     // stage the flux maps once per CTA: TMA bulk copy + mbarrier
-    size_t off = ((act_elems + (size_t)a.save_cap * NST * SIM_EP) * sizeof(T) + 15) & ~(size_t)15;
+    size_t off = (sim_sched_bytes<T>(a.step_cap, a.save_cap) + (act_elems + (size_t)a.save_cap * NST * SIM_EP) * sizeof(T) + 15) & ~(size_t)15;
     unsigned char *sm_lut = smem_raw + off;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut_bytes);
     if (e == 0) {
@@ -382,7 +420,6 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
   }
 #pragma unroll
   for (int i = 0; i < NODE; ++i) f[i] = (T)0;
-  bool have_f = false;
   T last[NST];
 #pragma unroll
   for (int i = 0; i < NST; ++i) last[i] = (T)0;
@@ -410,36 +447,32 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
       // ---- compute phase --------------------------------------------------------------------------------------
       const T *col0 = col - (long)ti.act_lo * A * SIM_EP;  // indexable by absolute ZOH index
       T *out_col = sm_out + e - (long)ti.save_begin * NST * SIM_EP;
-      const int n_end = ti.step_begin + ti.step_count;
-      // the schedule (word, dt, first save record) of step n+1 is fetched while step n is integrated
-      uint64_t w_next = __ldg(a.words + ti.step_begin);
-      T dt_next = __ldg(a.dts + ti.step_begin);
-      SaveRec<T> rec_next = a.recs[save_idx];
-      for (int n = ti.step_begin; n < n_end; ++n) {
+      auto fetch = [&](int idx, T *u) {
+#pragma unroll
+        for (int c = 0; c < A; ++c) u[c] = col0[(idx * A + c) * SIM_EP];
+      };
+      // the schedule entries (word, dt, first save record) of step i+1 are read while step i is integrated
+      const SaveRec<T> *srec = sched.recs - ti.save_begin;  // indexable by absolute save index
+      uint64_t w_next = sched.words[0];
+      T dt_next = sched.dts[0];
+      SaveRec<T> rec_next = srec[save_idx];
+      if (SOLVER == EXENV_TSIT5 && tile == 0) sim_first_derivative<Env, T>(w_next, y, f, p, pre, aux, fetch);
+      for (int i = 0; i < ti.step_count; ++i) {
         const uint64_t w = w_next;
         const T dt = dt_next;
         const SaveRec<T> rec = rec_next;
-        if (n + 1 < n_end) {
-          w_next = __ldg(a.words + n + 1);
-          dt_next = __ldg(a.dts + n + 1);
-          long nxt = save_idx + sched_saves(w);
-          if (nxt > a.n_save - 1) nxt = a.n_save - 1;
-          rec_next = a.recs[nxt];
-        }
-        sim_one_step<Env, SOLVER, T>(
-            w, dt, y, f, have_f, p, pre, aux, rec, a.recs, save_idx,
-            [&](int idx, T *u) {
+        w_next = sched.words[i + 1];
+        dt_next = sched.dts[i + 1];
+        rec_next = srec[save_idx + sched_saves(w)];
+        sim_one_step<Env, SOLVER, T>(w, dt, y, f, p, pre, aux, rec, srec, save_idx, fetch,
+                                     [&](long sidx, const T *st) {
+                                       T *o = out_col + (long)sidx * NST * SIM_EP;
 #pragma unroll
-              for (int c = 0; c < A; ++c) u[c] = col0[(idx * A + c) * SIM_EP];
-            },
-            [&](long sidx, const T *st) {
-              T *o = out_col + (long)sidx * NST * SIM_EP;
-#pragma unroll
-              for (int i = 0; i < NST; ++i) {
-                last[i] = st[i];
-                o[i * SIM_EP] = st[i];
-              }
-            });
+                                       for (int i2 = 0; i2 < NST; ++i2) {
+                                         last[i2] = st[i2];
+                                         o[i2 * SIM_EP] = st[i2];
+                                       }
+                                     });
       }
     } else {
       save_idx += ti.save_cnt;
@@ -449,7 +482,9 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
     // the next tile's actions travel while this tile's outputs are written
     const bool more = tile + 1 < a.n_tiles;
     if (more) {
-      prefetch_actions<Env, T>(a, a.tiles[tile + 1], sm_act, blk0, rows, warp, lane);
+      const SimTile tn = a.tiles[tile + 1];
+      prefetch_actions<Env, T>(a, tn, sm_act, blk0, rows, warp, lane);
+      prefetch_schedule<T>(a, tn, sched, e);
       cp_async_commit();
     }
 
@@ -508,9 +543,9 @@ __global__ void __launch_bounds__(SIM_E) sim_kernel(const SimK<T> a, const KPara
 
 // ---- launcher ----------------------------------------------------------------------------------------------------
 template <class Env, typename T>
-static size_t smem_bytes_t(const ExenvPlan &plan, int act_cap, int save_cap) {
+static size_t smem_bytes_t(const ExenvPlan &plan, int act_cap, int save_cap, int step_cap) {
   constexpr int NST = staged_values<Env>();
-  size_t n = (size_t)(act_cap * Env::A + save_cap * NST) * SIM_EP * sizeof(T);
+  size_t n = sim_sched_bytes<T>(step_cap, save_cap) + (size_t)(act_cap * Env::A + save_cap * NST) * SIM_EP * sizeof(T);
   if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) {
     n = (n + 15) & ~(size_t)15;
     n += plan.lut.bytes + 16;
@@ -543,6 +578,7 @@ static int launch_sim_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimS
   a.n_tiles = sch.n_tiles;
   a.act_cap = sch.act_cap;
   a.save_cap = sch.save_cap;
+  a.step_cap = sch.tile_steps;
   a.n_control = plan.desc.n_control;
   for (int j = 0; j < EXENV_MAX_CONTROL; ++j) a.control[j] = plan.desc.control[j];
   a.deadtime = plan.deadtime;
@@ -557,7 +593,7 @@ static int launch_sim_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimS
   a.lut_inv_dx = (T)plan.lut.inv_dx;
   a.lut_inv_dy = (T)plan.lut.inv_dy;
   KParams<T> kp = make_kparams<T>(plan);
-  const size_t smem = smem_bytes_t<Env, T>(plan, sch.act_cap, sch.save_cap);
+  const size_t smem = smem_bytes_t<Env, T>(plan, sch.act_cap, sch.save_cap, sch.tile_steps);
   auto kern = sim_kernel<Env, SOLVER, T, PER_ENV>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -614,20 +650,19 @@ int EXENV_CAT(launch_sim_, EXENV_SFX)(const ExenvPlan &plan, const ExenvSimArgs 
 }
 
 template <typename T>
-static size_t smem_dispatch(const ExenvPlan &plan, int ac, int sc) {
+static size_t smem_dispatch(const ExenvPlan &plan, int ac, int sc, int stc) {
   switch (plan.desc.env) {
-    case EXENV_PENDULUM: return smem_bytes_t<Pendulum<T>, T>(plan, ac, sc);
-    case EXENV_MASS_SPRING_DAMPER: return smem_bytes_t<MassSpringDamper<T>, T>(plan, ac, sc);
-    case EXENV_FLUID_TANK: return smem_bytes_t<FluidTank<T>, T>(plan, ac, sc);
-    case EXENV_CART_POLE: return smem_bytes_t<CartPole<T>, T>(plan, ac, sc);
-    case EXENV_ACROBOT: return smem_bytes_t<Acrobot<T>, T>(plan, ac, sc);
-    default: return smem_bytes_t<Pmsm<T, true>, T>(plan, ac, sc);
+    case EXENV_PENDULUM: return smem_bytes_t<Pendulum<T>, T>(plan, ac, sc, stc);
+    case EXENV_MASS_SPRING_DAMPER: return smem_bytes_t<MassSpringDamper<T>, T>(plan, ac, sc, stc);
+    case EXENV_FLUID_TANK: return smem_bytes_t<FluidTank<T>, T>(plan, ac, sc, stc);
+    case EXENV_CART_POLE: return smem_bytes_t<CartPole<T>, T>(plan, ac, sc, stc);
+    case EXENV_ACROBOT: return smem_bytes_t<Acrobot<T>, T>(plan, ac, sc, stc);
+    default: return smem_bytes_t<Pmsm<T, true>, T>(plan, ac, sc, stc);
   }
 }
 
-size_t EXENV_CAT(sim_smem_bytes_, EXENV_SFX)(const ExenvPlan &plan, int block_envs, int act_cap, int save_cap) {
-  (void)block_envs;
-  return smem_dispatch<EXENV_REAL>(plan, act_cap, save_cap);
+size_t EXENV_CAT(sim_smem_bytes_, EXENV_SFX)(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap) {
+  return smem_dispatch<EXENV_REAL>(plan, act_cap, save_cap, step_cap);
 }
 
 }  // namespace exenv

@@ -61,14 +61,51 @@ EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, int dea
 
 // One solver step + its saves.
 //   y[NODE]      ODE state, updated in place
-//   f[NODE]      Tsit5 FSAL derivative carried between steps (have_f tells whether it is valid)
-//   fetch(idx,u) physical action of ZOH index idx (absolute); called once per distinct index of the step
+//   f[NODE]      Tsit5: FSAL derivative at (t0, y); valid on entry (the caller evaluates it once before the first
+//                step, as diffrax does on `first_step`), replaced by the stage-7 derivative on exit
+//   fetch(idx,u) physical action of ZOH index idx (absolute)
 //   sink(save_index, staged[NST]) receives every saved sample, already wrapped / clipped (+ torque, PMSM buffers)
 //   rec0 / recs  per-save dense-output records: rec0 = recs[save_idx] (prefetched by the caller one step ahead so its
 //                latency is off the critical path), further saves of the same step read recs[] directly
 // Divisions by parameter-only denominators use the prepared reciprocals (div_inv<true>), see exenv_math.cuh.
+template <class Env, int SOLVER, typename T, class Fetch>
+EX_HD void sim_save_one(const SaveRec<T> &rec, const T *y, const T *y1, const T (*k)[Env::NODE], const T *p,
+                        typename Env::Aux &aux, long save_idx, Fetch &&fetch, T *st) {
+  constexpr int NODE = Env::NODE, A = Env::A;
+  T ysv[NODE];
+  if constexpr (SOLVER == EXENV_EULER) {  // LocalLinearInterpolation
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) ysv[i] = y[i] + rec.v[0] * (y1[i] - y[i]);
+  } else {  // _Tsit5Interpolation
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) {
+      T acc = rec.v[0] * k[0][i];
+#pragma unroll
+      for (int j = 1; j < 7; ++j) acc += rec.v[j] * k[j][i];
+      ysv[i] = y[i] + acc;
+    }
+  }
+  Env::post(ysv);
+  if constexpr (Env::IS_PMSM) {
+    st[0] = ysv[2];
+    st[1] = ysv[0];
+    st[2] = ysv[1];
+    st[3] = Env::torque(ysv[0], ysv[1], p, aux);
+    // u_dq buffer leaves of saved state j: vstack([buffer]*deadtime, clipped actions)[j]; zeros when
+    // deadtime == 0 (pmsm_env.py:785-791) -- the same dead-time shifted sequence the solver reads
+    T ub[A];
+    ub[0] = ub[1] = (T)0;
+    if (aux.deadtime > 0) fetch((int)save_idx, ub);
+    st[4] = ub[0];
+    st[5] = ub[1];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) st[i] = ysv[i];
+  }
+}
+
 template <class Env, int SOLVER, typename T, class Fetch, class Sink>
-EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, const typename Env::Pre &pre,
+EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename Env::Pre &pre,
                         typename Env::Aux &aux, const SaveRec<T> &rec0, const SaveRec<T> *recs, long &save_idx,
                         Fetch &&fetch, Sink &&sink) {
   constexpr int NODE = Env::NODE, A = Env::A, NST = staged_values<Env>();
@@ -84,83 +121,43 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, bool &have_f, const T *p, 
       y1[i] = y[i] + k[0][i];
     }
   } else {  // diffrax.Tsit5 with FSAL
-    // the (at most four) distinct ZOH actions of this step, then a warp-uniform select per stage
-    T ua[4][A];
-    const int dmax = sched_dmax(w);
-    fetch(base, ua[0]);
-#pragma unroll
-    for (int d = 1; d < 4; ++d) {
-      if (d <= dmax) {
-        fetch(base + d, ua[d]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < A; ++c) ua[d][c] = ua[0][c];
-      }
-    }
-    auto stage_u = [&](int stage, T *u) {
-      const int d = sched_delta(w, stage);
-#pragma unroll
-      for (int c = 0; c < A; ++c) u[c] = d == 0 ? ua[0][c] : (d == 1 ? ua[1][c] : (d == 2 ? ua[2][c] : ua[3][c]));
-    };
-    if (!have_f) {  // evaluated on diffrax's `first_step`
-      T u[A];
-      stage_u(0, u);
-      Env::template rhs<true>(y, u, p, pre, aux, f);
-      have_f = true;
-    }
     T fl[NODE];
     tsit5_step<T, NODE>(
         y, f, dt,
         [&](int stage, const T *ys, T *fo) {
           T u[A];
-          stage_u(stage, u);
+          fetch(base + sched_delta(w, stage), u);
           Env::template rhs<true>(ys, u, p, pre, aux, fo);
         },
         y1, fl, k);
 #pragma unroll
     for (int i = 0; i < NODE; ++i) f[i] = fl[i];
   }
-  // SaveAt(ts): dense output (LocalLinearInterpolation / _Tsit5Interpolation) at the scheduled abscissae
+  // SaveAt(ts): dense output at the scheduled abscissae; one save per step is the common case
   const int ns = sched_saves(w);
-  for (int q = 0; q < ns; ++q) {
-    SaveRec<T> rec = rec0;
-    if (q > 0) rec = recs[save_idx];
-    T ysv[NODE];
-    if constexpr (SOLVER == EXENV_EULER) {
-#pragma unroll
-      for (int i = 0; i < NODE; ++i) ysv[i] = y[i] + rec.v[0] * (y1[i] - y[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NODE; ++i) {
-        T acc = rec.v[0] * k[0][i];
-#pragma unroll
-        for (int j = 1; j < 7; ++j) acc += rec.v[j] * k[j][i];
-        ysv[i] = y[i] + acc;
-      }
-    }
-    Env::post(ysv);
+  if (ns > 0) {
     T st[NST];
-    if constexpr (Env::IS_PMSM) {
-      st[0] = ysv[2];
-      st[1] = ysv[0];
-      st[2] = ysv[1];
-      st[3] = Env::torque(ysv[0], ysv[1], p, aux);
-      // u_dq buffer leaves of saved state j: vstack([buffer]*deadtime, clipped actions)[j]; zeros when
-      // deadtime == 0 (pmsm_env.py:785-791) -- the same dead-time shifted sequence the solver reads
-      T ub[A];
-      ub[0] = ub[1] = (T)0;
-      if (aux.deadtime > 0) fetch((int)save_idx, ub);
-      st[4] = ub[0];
-      st[5] = ub[1];
-    } else {
-#pragma unroll
-      for (int i = 0; i < NODE; ++i) st[i] = ysv[i];
-    }
+    sim_save_one<Env, SOLVER, T>(rec0, y, y1, k, p, aux, save_idx, fetch, st);
     sink(save_idx, st);
     ++save_idx;
+    for (int q = 1; q < ns; ++q) {
+      const SaveRec<T> rec = recs[save_idx];
+      sim_save_one<Env, SOLVER, T>(rec, y, y1, k, p, aux, save_idx, fetch, st);
+      sink(save_idx, st);
+      ++save_idx;
+    }
   }
 #pragma unroll
   for (int i = 0; i < NODE; ++i) y[i] = y1[i];
+}
+
+// FSAL derivative for the very first step (diffrax evaluates it when `first_step` is set).
+template <class Env, typename T, class Fetch>
+EX_HD void sim_first_derivative(uint64_t w0, const T *y, T *f, const T *p, const typename Env::Pre &pre,
+                                typename Env::Aux &aux, Fetch &&fetch) {
+  T u[Env::A];
+  fetch(sched_base(w0) + sched_delta(w0, 0), u);
+  Env::template rhs<true>(y, u, p, pre, aux, f);
 }
 
 }  // namespace exenv

@@ -92,19 +92,19 @@ static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, 
       for (int i = 0; i < NODE; ++i) y[i] = s0[i];
     }
     for (int i = 0; i < NODE; ++i) f[i] = 0;
-    bool have_f = false;
     long save_idx = 0;
     const typename Env::Pre pre = Env::precompute(p);
     const T adv = (T)((dead_d + 0.5) * d->tau), lin_stop = (T)(d->tau * (double)(n_actions - 1));
+    auto fetch = [&](int idx, T *u) {
+      const long raw = (long)idx - dead;
+      const T *src = actions + (b * n_actions + (raw < 0 ? 0 : raw)) * A;
+      prepare_action<Env, T>(idx, src, s0, p, dead, n_actions, adv, lin_stop, u);
+    };
+    if (SOLVER == EXENV_TSIT5) sim_first_derivative<Env, T>(words[0], y, f, p, pre, aux, fetch);
     for (long n = 0; n < n_steps; ++n) {
       sim_one_step<Env, SOLVER, T>(
-          words[n], (T)dts[n], y, f, have_f, p, pre, aux, recs[(size_t)(save_idx < n_save ? save_idx : n_save - 1)],
-          recs.data(), save_idx,
-          [&](int idx, T *u) {
-            const long raw = (long)idx - dead;
-            const T *src = actions + (b * n_actions + (raw < 0 ? 0 : raw)) * A;
-            prepare_action<Env, T>(idx, src, s0, p, dead, n_actions, adv, lin_stop, u);
-          },
+          words[n], (T)dts[n], y, f, p, pre, aux, recs[(size_t)(save_idx < n_save ? save_idx : n_save - 1)],
+          recs.data(), save_idx, fetch,
           [&](long sidx, const T *st) {
             for (int i = 0; i < NST; ++i) traj[i][b * n_save + sidx] = st[i];
           });
