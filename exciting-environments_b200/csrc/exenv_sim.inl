@@ -163,49 +163,42 @@ __device__ __forceinline__ int pmsm_obs_field(int o) {
   return (o == 0) ? 3 : (o == 1) ? 4 : (o == 2) ? 6 : (o == 3) ? 5 : (o == 6) ? 0 : (o == 7) ? 1 : 2;
 }
 
-// Fast row writer: control_state == [], no epilogue, shared parameters, at most 32 saves in the tile.
+// Fast row writer: control_state == [], no epilogue, shared parameters.
 // A warp-wide store covers 32 consecutive scalars of one environment row when the tile holds more than 16 saves;
 // shorter tiles pack 2 or 4 rows into one store so that lanes stay busy.  A lane keeps a fixed (slot, observation
-// column), so its normalisation constants and smem/global offsets are loop invariants.
+// column), so its normalisation constants and smem/global offsets are loop invariants.  Rows are processed four at
+// a time (four shared-memory loads in flight before the first store) to keep the LDS latency off the critical path.
 template <class Env, typename T>
-__device__ __forceinline__ void store_tile_fast(const SimK<T> &a, const KParams<T> &kp, const SimTile &ti,
+__device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams<T> &kp, int save_begin, int cnt,
+                                                 const T *sm_out, long blk0, int rows, int warp, int lane);
+
+template <class Env, typename T>
+__device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams<T> &kp, int save_begin, int cnt,
+                                                 const T *sm_out, long blk0, int rows, int warp, int lane);
+
+// Long tiles (more than 32 saves): every environment row receives its whole run of `cnt` samples in consecutive
+// warp-wide stores (row outer, 32-slot chunks inner), so that HBM sees segments of cnt * 4 bytes (leaves) and
+// cnt * O * 4 bytes (observations) instead of isolated 128-byte lines.
+template <class Env, typename T>
+__device__ __forceinline__ void store_tile_long(const SimK<T> &a, const KParams<T> &kp, const SimTile &ti,
                                                 const T *sm_out, long blk0, int rows, int warp, int lane) {
   constexpr int D = Env::D, O = Env::O, NST = staged_values<Env>();
+  constexpr int LO = (O == 1) ? 0 : (O == 2) ? 1 : (O == 4) ? 2 : 3;
   const int cnt = ti.save_cnt;
   const T *pn = kp.v + Env::NSTATIC;
-  const int lp = cnt > 16 ? 5 : (cnt > 8 ? 4 : 3);  // log2 of the padded slot count P
-  // ---- trajectory leaves: P slots per row, 32 / P rows per warp-wide store
-  {
-    const int k = lane & ((1 << lp) - 1), rs = lane >> lp, R = 32 >> lp;
-    const bool on = k < cnt;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      T *leaf = a.traj[d];
-      if (!leaf) continue;
-      if (Env::IS_PMSM && d == 6) {  // omega_el: constant per environment, broadcast over time
-        for (int r = warp * R + rs; r < rows; r += SIM_NW * R)
-          if (on) leaf[(blk0 + r) * a.n_save + ti.save_begin + k] = __ldg(a.sin[6] + blk0 + r);
-        continue;
-      }
-      const int v = Env::IS_PMSM ? ((d >= 2) ? d - 2 : d + 4) : d;
-      const T *src = sm_out + (k * NST + v) * SIM_EP + warp * R + rs;
-      T *dst = leaf + (blk0 + warp * R + rs) * a.n_save + ti.save_begin + k;
-      const long stride = (long)SIM_NW * R * a.n_save;
-      for (int r = warp * R + rs; r < rows; r += SIM_NW * R) {
-        if (on) *dst = *src;
-        src += SIM_NW * R;
-        dst += stride;
-      }
+  for (int d = 0; d < D; ++d) {
+    T *leaf = a.traj[d];
+    if (!leaf) continue;
+    const int v = Env::IS_PMSM ? ((d >= 2) ? d - 2 : d + 4) : d;
+    for (int r = warp; r < rows; r += SIM_NW) {
+      T *dst = leaf + (blk0 + r) * a.n_save + ti.save_begin;
+      const T om = (Env::IS_PMSM && d == 6) ? __ldg(a.sin[6] + blk0 + r) : (T)0;
+      for (int k = lane; k < cnt; k += 32)
+        dst[k] = (Env::IS_PMSM && d == 6) ? om : sm_out[(k * NST + v) * SIM_EP + r];
     }
   }
-  // ---- observation rows: P * O scalars per row (O divides 32: a lane owns one observation column)
   {
-    constexpr int LO = (O == 1) ? 0 : (O == 2) ? 1 : (O == 4) ? 2 : 3;
-    const int lrow = lp + LO;                   // log2 of the padded row length
-    const int llanes = lrow < 5 ? lrow : 5;     // log2 lanes spent on one row
-    const int iters = 1 << (lrow - llanes);     // warp-wide stores per row
-    const int R = 32 >> llanes;                 // rows per warp-wide store
-    const int jl = lane & ((1 << llanes) - 1), rs = lane >> llanes;
     const int o = lane & (O - 1);
     int fld = o;
     if constexpr (Env::IS_PMSM) fld = pmsm_obs_field(o);
@@ -219,27 +212,126 @@ __device__ __forceinline__ void store_tile_fast(const SimK<T> &a, const KParams<
       }
     const InvDiv<T> sdiv = make_invdiv<T>(span);
     const int v = Env::IS_PMSM ? ((fld >= 2) ? fld - 2 : fld + 4) : fld;
-    const long stride = (long)SIM_NW * R * a.n_save * O;
+    const int n_el = cnt * O;
+    for (int r = warp; r < rows; r += SIM_NW) {
+      T *dst = a.obs + ((blk0 + r) * a.n_save + ti.save_begin) * O;
+      for (int j = lane; j < n_el; j += 32) {
+        const int k = j >> LO;
+        T x;
+        if (Env::IS_PMSM && fld == 6) x = __ldg(a.sin[6] + blk0 + r);
+        else x = sm_out[(k * NST + v) * SIM_EP + r];
+        T val;
+        if constexpr (Env::IS_PMSM) {
+          val = (o == 4) ? Mth<T>::cos(x) : (o == 5) ? Mth<T>::sin(x) : norm_inv<true, T>(x, mn, sdiv);
+        } else {
+          val = norm_inv<true, T>(x, mn, sdiv);
+        }
+        dst[j] = val;
+      }
+    }
+  }
+}
+
+template <class Env, typename T>
+__device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams<T> &kp, int save_begin, int cnt,
+                                                 const T *sm_out, long blk0, int rows, int warp, int lane);
+
+template <class Env, typename T>
+__device__ __forceinline__ void store_tile_fast(const SimK<T> &a, const KParams<T> &kp, const SimTile &ti,
+                                                const T *sm_out, long blk0, int rows, int warp, int lane) {
+  constexpr int NST = staged_values<Env>();
+  for (int c0 = 0; c0 < ti.save_cnt; c0 += 32) {  // 32 slots per pass: one full 128-byte store per leaf row
+    const int cnt = ti.save_cnt - c0 < 32 ? ti.save_cnt - c0 : 32;
+    store_chunk_fast<Env, T>(a, kp, ti.save_begin + c0, cnt, sm_out + (size_t)c0 * NST * SIM_EP, blk0, rows, warp, lane);
+  }
+}
+
+template <class Env, typename T>
+__device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams<T> &kp, int save_begin, int cnt,
+                                                 const T *sm_out, long blk0, int rows, int warp, int lane) {
+  constexpr int D = Env::D, O = Env::O, NST = staged_values<Env>(), U = 4;
+  const T *pn = kp.v + Env::NSTATIC;
+  const int lp = cnt > 16 ? 5 : (cnt > 8 ? 4 : 3);  // log2 of the padded slot count P
+  // ---- trajectory leaves: P slots per row, 32 / P rows per warp-wide store
+  {
+    const int k = lane & ((1 << lp) - 1), rs = lane >> lp, R = 32 >> lp;
+    const bool on = k < cnt;
+    const int rstep = SIM_NW * R;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      T *leaf = a.traj[d];
+      if (!leaf) continue;
+      if (Env::IS_PMSM && d == 6) {  // omega_el: constant per environment, broadcast over time
+        for (int r = warp * R + rs; r < rows; r += rstep)
+          if (on) leaf[(blk0 + r) * a.n_save + save_begin + k] = __ldg(a.sin[6] + blk0 + r);
+        continue;
+      }
+      const int v = Env::IS_PMSM ? ((d >= 2) ? d - 2 : d + 4) : d;
+      const T *src = sm_out + (k * NST + v) * SIM_EP + warp * R + rs;
+      T *dst = leaf + (blk0 + warp * R + rs) * a.n_save + save_begin + k;
+      const long stride = (long)rstep * a.n_save;
+      for (int r = warp * R + rs; r < rows; r += U * rstep) {
+        T x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = (on && r + u * rstep < rows) ? src[u * rstep] : (T)0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (on && r + u * rstep < rows) dst[u * stride] = x[u];
+        src += U * rstep;
+        dst += U * stride;
+      }
+    }
+  }
+  // ---- observation rows: P * O scalars per row (O divides 32: a lane owns one observation column)
+  {
+    constexpr int LO = (O == 1) ? 0 : (O == 2) ? 1 : (O == 4) ? 2 : 3;
+    const int lrow = lp + LO;                   // log2 of the padded row length
+    const int llanes = lrow < 5 ? lrow : 5;     // log2 lanes spent on one row
+    const int iters = 1 << (lrow - llanes);     // warp-wide stores per row
+    const int R = 32 >> llanes;                 // rows per warp-wide store
+    const int jl = lane & ((1 << llanes) - 1), rs = lane >> llanes;
+    const int o = lane & (O - 1);
+    const int rstep = SIM_NW * R;
+    int fld = o;
+    if constexpr (Env::IS_PMSM) fld = pmsm_obs_field(o);
+    T mn = pn[0];
+    T span = pn[1] - pn[0];
+#pragma unroll
+    for (int i = 1; i < D; ++i)
+      if (fld == i) {
+        mn = pn[2 * i];
+        span = pn[2 * i + 1] - pn[2 * i];
+      }
+    const InvDiv<T> sdiv = make_invdiv<T>(span);
+    const int v = Env::IS_PMSM ? ((fld >= 2) ? fld - 2 : fld + 4) : fld;
+    const long stride = (long)rstep * a.n_save * O;
     for (int it = 0; it < iters; ++it) {
       const int j = it * 32 + jl, k = j >> LO;
       const bool on = k < cnt;
       const T *src = sm_out + (k * NST + v) * SIM_EP + warp * R + rs;
-      T *dst = a.obs + ((blk0 + warp * R + rs) * a.n_save + ti.save_begin) * O + j;
-      for (int r = warp * R + rs; r < rows; r += SIM_NW * R) {
-        if (on) {
-          T x;
-          if (Env::IS_PMSM && fld == 6) x = __ldg(a.sin[6] + blk0 + r);
-          else x = *src;
-          T val;
-          if constexpr (Env::IS_PMSM) {
-            val = (o == 4) ? Mth<T>::cos(x) : (o == 5) ? Mth<T>::sin(x) : norm_inv<true, T>(x, mn, sdiv);
-          } else {
-            val = norm_inv<true, T>(x, mn, sdiv);
-          }
-          *dst = val;
+      T *dst = a.obs + ((blk0 + warp * R + rs) * a.n_save + save_begin) * O + j;
+      for (int r = warp * R + rs; r < rows; r += U * rstep) {
+        T x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool act = on && r + u * rstep < rows;
+          if (Env::IS_PMSM && fld == 6) x[u] = act ? __ldg(a.sin[6] + blk0 + r + u * rstep) : (T)0;
+          else x[u] = act ? src[u * rstep] : (T)0;
         }
-        src += SIM_NW * R;
-        dst += stride;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (on && r + u * rstep < rows) {
+            T val;
+            if constexpr (Env::IS_PMSM) {
+              val = (o == 4) ? Mth<T>::cos(x[u]) : (o == 5) ? Mth<T>::sin(x[u]) : norm_inv<true, T>(x[u], mn, sdiv);
+            } else {
+              val = norm_inv<true, T>(x[u], mn, sdiv);
+            }
+            dst[u * stride] = val;
+          }
+        }
+        src += U * rstep;
+        dst += U * stride;
       }
     }
   }
@@ -491,7 +583,7 @@ __global__ void __launch_bounds__(SIM_E)
     // ---- store phase: rows of the batch-major outputs, lanes along time ---------------------------------------
     if (ti.save_cnt > 0) {
       if constexpr (!PER_ENV) {
-        if (fast_store && ti.save_cnt <= 32)
+        if (fast_store)
           store_tile_fast<Env, T>(a, kp, ti, sm_out, blk0, rows, warp, lane);
         else
           store_tile_generic<Env, T, false>(a, kp, ti, sm_out, blk0, rows, warp, lane);
