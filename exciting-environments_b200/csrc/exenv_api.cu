@@ -236,15 +236,25 @@ static int build_schedule(const ExenvPlan &plan, int64_t n_actions, double obs_d
                                       : build_schedule_t<float>(plan, n_actions, obs_dt, act_dt, tile_steps, out);
 }
 
-// Tile length: as many solver steps as fit the per-CTA shared-memory share that keeps >= 16 warps per SM resident.
-static int auto_tile_steps(const ExenvPlan &plan, int E) {
-  const size_t sm_total = 227 * 1024;
-  int ctas = std::max(1, 512 / E);
-  if (plan.desc.dtype == EXENV_F64 && ctas > 1) ctas = std::max(1, 384 / E);
-  const size_t budget = sm_total / ctas - 1024;
-  const int cand[] = {64, 48, 32, 24, 16, 12, 8, 4, 2, 1};
+// Tile length.  Longer tiles mean longer contiguous row segments in HBM (128 B per leaf row at 32 fp32 saves) but
+// more shared memory per CTA, i.e. fewer resident warps.  Measured on B200 (tools/sweep_tiles.sh, profiles/README.md):
+// light right-hand sides (mass-spring-damper, fluid tank, any Euler run) are bound by the memory access pattern and
+// want 32-step tiles at 4 CTAs/SM; transcendental-heavy ones (pendulum, cart-pole Tsit5) want more resident warps;
+// acrobot and PMSM are instruction bound and take the smallest tiles.
+static int auto_tile_steps(const ExenvPlan &plan, int /*E*/) {
+  const int env = plan.desc.env;
+  const bool tsit = plan.desc.solver == EXENV_TSIT5;
+  size_t budget = 56 * 1024;
+  if (env == EXENV_ACROBOT || env == EXENV_PMSM)
+    budget = 36 * 1024;
+  else if (tsit && (env == EXENV_PENDULUM || env == EXENV_CART_POLE))
+    budget = 44 * 1024;
+  const int cand[] = {32, 24, 16, 12, 8};
   for (int k : cand)
     if (sim_smem_bytes(plan, k, k + 3, k) <= budget) return k;
+  const int small[] = {8, 4, 2, 1};
+  for (int k : small)
+    if (sim_smem_bytes(plan, k, k + 3, k) <= 200 * 1024) return k;
   return 1;
 }
 
