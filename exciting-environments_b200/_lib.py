@@ -68,6 +68,11 @@ class ExenvSimArgs(C.Structure):
     ]
 
 
+class ExenvEpilogueArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("state", C.c_void_p * MAX_PHYS), ("ref", C.c_void_p * MAX_PHYS),
+                ("reward", C.c_void_p), ("truncated", C.c_void_p), ("terminated", C.c_void_p)]
+
+
 class ExenvScheduleInfo(C.Structure):
     _fields_ = [("n_save", C.c_int64), ("n_steps", C.c_int64), ("n_tiles", C.c_int32), ("act_cap", C.c_int32),
                 ("save_cap", C.c_int32), ("tile_steps", C.c_int32)]
@@ -84,7 +89,7 @@ class ExenvResetArgs(C.Structure):
 SYMBOLS = [
     "exenv_abi_version", "exenv_last_error", "exenv_env_dims", "exenv_launch_count", "exenv_plan_create",
     "exenv_plan_destroy", "exenv_step", "exenv_sim_ahead_shape", "exenv_sim_ahead", "exenv_sim_ahead_host",
-    "exenv_reset_pack", "exenv_schedule_build",
+    "exenv_reset_pack", "exenv_schedule_build", "exenv_epilogue",
 ]
 
 
@@ -122,6 +127,7 @@ def lib():
                                             C.POINTER(C.c_int64)]
         L.exenv_reset_pack.argtypes = [C.c_void_p, C.POINTER(ExenvResetArgs), C.c_void_p]
         L.exenv_env_dims.argtypes = [C.c_int32, C.POINTER(ExenvDims)]
+        L.exenv_epilogue.argtypes = [C.c_void_p, C.POINTER(ExenvEpilogueArgs), C.c_void_p]
         L.exenv_schedule_build.argtypes = [C.POINTER(ExenvDesc), C.c_int64, C.c_double, C.c_double, C.c_int32,
                                            C.POINTER(ExenvScheduleInfo), C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]

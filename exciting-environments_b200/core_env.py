@@ -503,6 +503,59 @@ class CoreEnvironment:
         return self._sim_impl(self.env_properties, self.batch_size, init_state, actions, obs_stepsize,
                               action_stepsize, epilogue=True, **kw)
 
+    # ---- reward / truncated / terminated of materialised states ------------------------------------------------------
+    def _epilogue_impl(self, phys_leaves, ref_leaves, n):
+        """generate_reward / generate_truncated / generate_terminated over `n` states given as flat leaves."""
+        plan = self._plan()
+        dev, dt = self.device, self.dtype
+        a = _lib.ExenvEpilogueArgs()
+        a.batch = n
+        keep = []
+        for i in range(self.physical_state_dim):
+            x = self._as(phys_leaves[i]).reshape(-1)
+            keep.append(x)
+            a.state[i] = x.data_ptr()
+            if self.control_state:
+                r = self._as(ref_leaves[i]).reshape(-1)
+                keep.append(r)
+                a.ref[i] = r.data_ptr()
+        rew = torch.empty(n, dtype=dt, device=dev)
+        trunc = torch.empty((n, self.n_trunc), dtype=torch.bool, device=dev)
+        term = torch.empty(n, dtype=torch.bool, device=dev)
+        a.reward, a.truncated, a.terminated = rew.data_ptr(), trunc.data_ptr(), term.data_ptr()
+        _lib.check(_lib.lib().exenv_epilogue(plan.handle, C.byref(a), self._stream()))
+        return rew, trunc, term
+
+    def vmap_generate_reward_truncated_terminated(self, state):
+        """The GymWrapper epilogue for a batched state (reference gym_wrapper.py:117-126):
+        ``(reward (B, 1), truncated (B, n_trunc), terminated (B, 1))``."""
+        B = self.batch_size
+        phys = [getattr(state.physical_state, n) for n in self.PHYS_FIELDS]
+        refs = [getattr(state.reference, n) for n in self.PHYS_FIELDS]
+        rew, trunc, term = self._epilogue_impl(phys, refs, B)
+        return rew.reshape(B, 1), trunc, term.reshape(B, 1)
+
+    def vmap_generate_rew_trunc_term_ahead(self, states, actions):
+        """Reward, truncated and terminated flags for data generated by ``vmap_sim_ahead`` (reference
+        core_env.py:618-647): truncated for every saved state ``(B, N+1, n_trunc)``, reward / terminated for
+        ``states[1:]`` ``(B, N, 1)``.  (``actions`` does not enter any reward of the six environments.)"""
+        shape = tuple(actions.shape)
+        assert len(shape) == 3, "The actions need to have three dimensions: (batch_size, n_action_steps, action_dim)"
+        assert (
+            shape[0] == self.batch_size
+        ), f"The first dimension does not correspond to the batch size which is {self.batch_size}, but {shape[0]} is given"
+        assert (
+            shape[-1] == self.action_dim
+        ), f"The last dimension does not correspond to the action dim which is {self.action_dim}, but {shape[-1]} is given"
+        B = self.batch_size
+        first = getattr(states.physical_state, self.PHYS_FIELDS[0])
+        NS = first.shape[1]
+        phys = [getattr(states.physical_state, n).contiguous() for n in self.PHYS_FIELDS]
+        refs = [torch.as_tensor(getattr(states.reference, n), device=self.device).expand(B, NS).contiguous()
+                for n in self.PHYS_FIELDS] if self.control_state else [None] * len(phys)
+        rew, trunc, term = self._epilogue_impl(phys, refs, B * NS)
+        return (rew.reshape(B, NS)[:, 1:, None], trunc.reshape(B, NS, self.n_trunc), term.reshape(B, NS)[:, 1:, None])
+
     # ---- single-environment API (reference core_env.py:361-488): the batched kernels with B = 1 -------------------
     def _wrap1(self, state):
         """Scalar-leaf State -> (1,) leaves."""

@@ -71,6 +71,8 @@ int launch_step_f32(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t 
 int launch_step_f64(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
 int launch_reset_f32(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream);
 int launch_reset_f64(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream);
+int launch_epilogue_f32(const ExenvPlan &plan, const ExenvEpilogueArgs &a, cudaStream_t stream);
+int launch_epilogue_f64(const ExenvPlan &plan, const ExenvEpilogueArgs &a, cudaStream_t stream);
 int launch_sim_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_sim_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 size_t sim_smem_bytes_f32(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);

@@ -289,6 +289,88 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetK<T> a, const KPa
     if (o < OW) a.obs[b * OW + o] = ob[o];
 }
 
+// reward / truncated / terminated of given states: one thread per state.
+template <typename T>
+struct EpiK {
+  long B;
+  const T *s[EXENV_MAX_PHYS];
+  const T *ref[EXENV_MAX_PHYS];
+  T *reward;
+  uint8_t *trunc;
+  uint8_t *term;
+  int n_control;
+  int control[EXENV_MAX_CONTROL];
+};
+
+template <class Env, typename T>
+__global__ void __launch_bounds__(256) epilogue_kernel(const EpiK<T> a, const KParams<T> kp) {
+  constexpr int D = Env::D, O = Env::O;
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const T *p = kp.v;
+  T s[D], r[D], ob[O + EXENV_MAX_CONTROL];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    s[d] = __ldg(a.s[d] + b);
+    r[d] = a.n_control > 0 ? __ldg(a.ref[d] + b) : (T)0;
+  }
+  observe<Env, T>(s, p, ob);
+#pragma unroll
+  for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
+    if (j < a.n_control) ob[O + j] = norm_field<Env, T>(a.control[j], r, p);
+  const int nt = trunc_dim<Env>(a.n_control);
+  bool t0 = false;
+#pragma unroll
+  for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
+    if (i < nt) {
+      const bool tv = trunc_entry<Env, T>(i, s, ob, p);
+      if (i == 0) t0 = tv;
+      if (a.trunc) a.trunc[b * nt + i] = tv;
+    }
+  const T rw = a.n_control > 0 ? reward_of<Env, T>(s, r, p, a.n_control, a.control) : (T)0;
+  if (a.reward) a.reward[b] = rw;
+  if (a.term) a.term[b] = terminated_of<Env, T>(rw, t0);
+}
+
+template <class Env, typename T>
+static int launch_epilogue_t(const ExenvPlan &plan, const ExenvEpilogueArgs &x, cudaStream_t stream) {
+  EpiK<T> a{};
+  a.B = x.batch;
+  for (int d = 0; d < Env::D; ++d) {
+    a.s[d] = (const T *)x.state[d];
+    a.ref[d] = (const T *)x.ref[d];
+  }
+  a.reward = (T *)x.reward;
+  a.trunc = x.truncated;
+  a.term = x.terminated;
+  a.n_control = plan.desc.n_control;
+  for (int j = 0; j < EXENV_MAX_CONTROL; ++j) a.control[j] = plan.desc.control[j];
+  const KParams<T> kp = make_kparams<T>(plan);
+  const unsigned grid = (unsigned)((x.batch + 255) / 256);
+  epilogue_kernel<Env, T><<<grid, 256, 0, stream>>>(a, kp);
+  g_launch_count++;
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("exenv_epilogue launch failed: %s", cudaGetErrorString(e));
+    return EXENV_ERR_CUDA;
+  }
+  return EXENV_OK;
+}
+
+int EXENV_CAT(launch_epilogue_, EXENV_SFX)(const ExenvPlan &plan, const ExenvEpilogueArgs &x, cudaStream_t st) {
+  using T = EXENV_REAL;
+  switch (plan.desc.env) {
+    case EXENV_PENDULUM: return launch_epilogue_t<Pendulum<T>, T>(plan, x, st);
+    case EXENV_MASS_SPRING_DAMPER: return launch_epilogue_t<MassSpringDamper<T>, T>(plan, x, st);
+    case EXENV_FLUID_TANK: return launch_epilogue_t<FluidTank<T>, T>(plan, x, st);
+    case EXENV_CART_POLE: return launch_epilogue_t<CartPole<T>, T>(plan, x, st);
+    case EXENV_ACROBOT: return launch_epilogue_t<Acrobot<T>, T>(plan, x, st);
+    case EXENV_PMSM: return launch_epilogue_t<Pmsm<T, false>, T>(plan, x, st);
+  }
+  set_error("unknown env %d", plan.desc.env);
+  return EXENV_ERR_INVALID;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------------------
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

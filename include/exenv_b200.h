@@ -12,6 +12,8 @@
  *                            pendulum_env.py:196-259) + vmap_generate_rew_trunc_term_ahead core_env.py:618-647
  *   exenv_reset_pack      <- CoreEnvironment.vmap_reset           core_env.py:664-687  (-> reset :361-391, init_state
  *                            e.g. pendulum_env.py:261-295) and vmap_generate_state_from_observation :689-705
+ *   exenv_epilogue        <- vmap(generate_reward / truncated / terminated) gym_wrapper.py:117-126 and
+ *                            vmap_generate_rew_trunc_term_ahead core_env.py:618-647 on materialised states
  *   exenv_sim_ahead_host  <- the same vmap_sim_ahead call made with HOST buffers (what a CPU-JAX caller holds);
  *                            pipelines H2D / kernel / D2H over batch chunks.
  *
@@ -165,6 +167,20 @@ int exenv_sim_ahead_shape(exenv_plan_t plan, int64_t n_actions, double obs_steps
 int exenv_sim_ahead(exenv_plan_t plan, const ExenvSimArgs *args, void *stream);
 /* Same call with HOST buffers (pinned or pageable); chunk_envs environments per pipeline stage (0 = auto). */
 int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *host_args, int64_t chunk_envs);
+
+/* ---- reward / truncated / terminated of given states -------------------------------------------------------------
+ * generate_reward / generate_truncated / generate_terminated vmapped over `batch` states (gym_wrapper.py:117-126) and,
+ * applied to the flattened (B * (N+1),) leaves of a trajectory, CoreEnvironment.vmap_generate_rew_trunc_term_ahead
+ * (core_env.py:618-647; PMSM pmsm_env.py:803-849).  Shared parameters only. */
+typedef struct ExenvEpilogueArgs {
+  int64_t batch;
+  const void *state[EXENV_MAX_PHYS]; /* D leaves (batch,) */
+  const void *ref[EXENV_MAX_PHYS];   /* D reference leaves (batch,), required iff n_control > 0 */
+  void *reward;                      /* optional (batch,) */
+  uint8_t *truncated;                /* optional (batch, n_trunc) */
+  uint8_t *terminated;               /* optional (batch,) */
+} ExenvEpilogueArgs;
+int exenv_epilogue(exenv_plan_t plan, const ExenvEpilogueArgs *args, void *stream);
 
 /* Host-only diagnostic (needs no CUDA device): the emulated diffrax.diffeqsolve time bookkeeping for `desc` -- per
  * solver step the packed ZOH-index word and step length, per saved sample the dense-output abscissa, and the tile

@@ -232,3 +232,31 @@ def test_host_buffer_entry_point_equals_device_entry_point(excenvs):
     assert np.array_equal(h_obs, np_(obs))
     assert np.array_equal(h_traj[0], np_(states.physical_state.theta))
     assert np.array_equal(h_last[1], np_(last.physical_state.omega))
+
+
+@pytest.mark.parametrize("env,ctrl", [("pendulum", ["theta"]), ("cart_pole", ["theta", "deflection"]),
+                                      ("mass_spring_damper", []), ("fluid_tank", ["height"]), ("acrobot", ["omega_2"]),
+                                      ("pmsm", ["i_d", "i_q"]), ("pmsm", ["torque"])])
+def test_standalone_rew_trunc_term_ahead_equals_fused(excenvs, env, ctrl):
+    """vmap_generate_rew_trunc_term_ahead (reference core_env.py:618-647) on the materialised trajectory == the
+    outputs fused into the trajectory kernel == the oracle."""
+    rng = np.random.default_rng(3)
+    B, T = 257, 40
+    orc = O.Oracle(env, solver=O.TSIT5, dtype=np.float64, control_state=ctrl, tau=1e-4)
+    base = O.Oracle(env, dtype=np.float64)
+    st = random_state(base, B, rng, 0.6, pmsm_gentle=(env == "pmsm"))
+    refl = random_state(base, B, rng, 0.6)
+    acts = rng.uniform(-1, 1, (B, T, orc.A)) * (0.02 if env == "pmsm" else 1.0)
+    ref = orc.sim_ahead(st, acts, 1e-4, 1e-4, ref=refl if ctrl else None, epilogue=True)
+    e = make_env(excenvs, orc, B)
+    s0 = to_state(e, st, refl if ctrl else None)
+    a = torch.as_tensor(acts, device="cuda")
+    obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(s0, a, 1e-4, 1e-4)
+    rew2, trunc2, term2 = e.vmap_generate_rew_trunc_term_ahead(states, a)
+    assert rew2.shape == (B, T, 1) and trunc2.shape == (B, T + 1, orc.n_trunc) and term2.shape == (B, T, 1)
+    assert torch.allclose(rew, rew2, rtol=1e-12, atol=1e-14) and torch.equal(trunc, trunc2) and torch.equal(term, term2)
+    assert np.allclose(np_(rew)[..., 0], ref["reward"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(np_(term)[..., 0].astype(np.uint8), ref["terminated"])
+    # GymWrapper-style epilogue of a single batched state
+    r1, tr1, te1 = e.vmap_generate_reward_truncated_terminated(last)
+    assert torch.allclose(r1[:, 0], rew[:, -1, 0], rtol=1e-12, atol=1e-14) and torch.equal(tr1, trunc[:, -1])
