@@ -383,7 +383,11 @@ EX_HD T obs_entry(int o, const T *s, const T *p) {
 template <class Env, typename T>
 EX_HD void observe(const T *s, const T *p, T *obs) {
 #pragma unroll
-  for (int o = 0; o < Env::O; ++o) obs[o] = obs_entry<Env, T>(o, s, p);
+  for (int o = 0; o < Env::O; ++o) {
+    if (Env::IS_PMSM && (o == 4 || o == 5)) continue;
+    obs[o] = obs_entry<Env, T>(o, s, p);
+  }
+  if constexpr (Env::IS_PMSM) Mth<T>::sincos(s[2], &obs[5], &obs[4]);
 }
 
 // Normalised field `f` of a physical-state-shaped vector (state or reference).

@@ -303,7 +303,9 @@ __device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams
         span = pn[2 * i + 1] - pn[2 * i];
       }
     const InvDiv<T> sdiv = make_invdiv<T>(span);
-    const int v = Env::IS_PMSM ? ((fld >= 2) ? fld - 2 : fld + 4) : fld;
+    int v = Env::IS_PMSM ? ((fld >= 2) ? fld - 2 : fld + 4) : fld;
+    const bool raw = Env::IS_PMSM && (o == 4 || o == 5);  // staged cos(eps) / sin(eps): copied as they are
+    if (raw) v = o + 2;
     const long stride = (long)rstep * a.n_save * O;
     for (int it = 0; it < iters; ++it) {
       const int j = it * 32 + jl, k = j >> LO;
@@ -321,13 +323,8 @@ __device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (on && r + u * rstep < rows) {
-            T val;
-            if constexpr (Env::IS_PMSM) {
-              val = (o == 4) ? Mth<T>::cos(x[u]) : (o == 5) ? Mth<T>::sin(x[u]) : norm_inv<true, T>(x[u], mn, sdiv);
-            } else {
-              val = norm_inv<true, T>(x[u], mn, sdiv);
-            }
-            dst[u * stride] = val;
+            const T nv = norm_inv<true, T>(x[u], mn, sdiv);
+            dst[u * stride] = raw ? x[u] : nv;
           }
         }
         src += U * rstep;

@@ -18,10 +18,11 @@ EX_HD int sched_saves(uint64_t w) { return (int)((w >> 46) & 15ull); }
 EX_HD int sched_dmax(uint64_t w) { return (int)((w >> 50) & 3ull); }  // largest stage offset of the step
 
 // Number of values staged per save: the post-processed ODE state; PMSM: eps, i_d, i_q, torque, u_d_buffer,
-// u_q_buffer.
+// u_q_buffer, cos(eps), sin(eps) (the two observation entries that are not plain normalisations are evaluated once
+// by the owner thread instead of divergently by the row writer).
 template <class Env>
 constexpr int staged_values() {
-  return Env::IS_PMSM ? 6 : Env::NODE;
+  return Env::IS_PMSM ? 8 : Env::NODE;
 }
 
 // Per-save dense-output record built by the host (exenv_api.cu): Tsit5 -> the seven weights b_i(theta) of
@@ -98,6 +99,7 @@ EX_HD void sim_save_one(const SaveRec<T> &rec, const T *y, const T *y1, const T 
     if (aux.deadtime > 0) fetch((int)save_idx, ub);
     st[4] = ub[0];
     st[5] = ub[1];
+    Mth<T>::sincos(ysv[2], &st[7], &st[6]);  // obs entries cos(eps), sin(eps) (pmsm_env.py:900-902)
   } else {
 #pragma unroll
     for (int i = 0; i < NODE; ++i) st[i] = ysv[i];

@@ -72,7 +72,7 @@ def hc_sim(lib, orc, state, actions, obs_dt, act_dt, tile_steps=32):
     lut, keep = hc_lut(orc)
     B, T = actions.shape[0], actions.shape[1]
     info, words, dt, theta, tiles = ex._lib.schedule(d, T, obs_dt, act_dt, tile_steps)
-    nst = 6 if orc.env == "pmsm" else orc.node
+    nst = 8 if orc.env == "pmsm" else orc.node
     traj = [np.zeros((B, info.n_save), orc.dtype) for _ in range(nst)]
     actions = np.ascontiguousarray(actions, orc.dtype)
     lib.hc_sim(C.byref(d), C.byref(lut) if lut else None, C.c_long(B), C.c_long(T), C.c_long(info.n_save),
