@@ -276,7 +276,7 @@ __device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams
         for (int u = 0; u < U; ++u) x[u] = (on && r + u * rstep < rows) ? src[u * rstep] : (T)0;
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (on && r + u * rstep < rows) dst[u * stride] = x[u];
+          if (on && r + u * rstep < rows) __stcs(dst + u * stride, x[u]);
         src += U * rstep;
         dst += U * stride;
       }
@@ -324,7 +324,7 @@ __device__ __forceinline__ void store_chunk_fast(const SimK<T> &a, const KParams
         for (int u = 0; u < U; ++u) {
           if (on && r + u * rstep < rows) {
             const T nv = norm_inv<true, T>(x[u], mn, sdiv);
-            dst[u * stride] = raw ? x[u] : nv;
+            __stcs(dst + u * stride, raw ? x[u] : nv);
           }
         }
         src += U * rstep;
