@@ -19,6 +19,7 @@ MAX_PARAMS, MAX_CONTROL, MAX_PHYS, MAX_ODE = 32, 8, 8, 4
 EULER, TSIT5 = 0, 1
 F32, F64 = 0, 1
 FLAG_SATURATED = 1
+LAYOUT_BATCH_MAJOR, LAYOUT_TIME_MAJOR = 0, 1
 RESET_DEFAULT, RESET_FROM_NORM, RESET_FROM_OBS, RESET_FROM_STATE = 0, 1, 2, 3
 
 STATUS = {0: "EXENV_OK", -1: "EXENV_ERR_INVALID", -2: "EXENV_ERR_NULL", -3: "EXENV_ERR_ALIGN",
@@ -64,7 +65,7 @@ class ExenvSimArgs(C.Structure):
         ("traj", C.c_void_p * MAX_PHYS), ("last", C.c_void_p * MAX_PHYS), ("k_last", C.c_void_p * MAX_ODE),
         ("ref", C.c_void_p * MAX_PHYS),
         ("reward", C.c_void_p), ("truncated", C.c_void_p), ("terminated", C.c_void_p),
-        ("tile_steps", C.c_int32), ("block_envs", C.c_int32),
+        ("tile_steps", C.c_int32), ("block_envs", C.c_int32), ("layout", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -131,7 +132,7 @@ def lib():
         L.exenv_schedule_build.argtypes = [C.POINTER(ExenvDesc), C.c_int64, C.c_double, C.c_double, C.c_int32,
                                            C.POINTER(ExenvScheduleInfo), C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
-        assert L.exenv_abi_version() == 1
+        assert L.exenv_abi_version() == 2
         _lib = L
     return _lib
 

@@ -129,6 +129,18 @@ static int build_schedule_t(const ExenvPlan &plan, int64_t n_actions, double obs
       return EXENV_ERR_UNSUPPORTED;
     }
     w |= (uint64_t)ns << 46;
+    {  // window of consecutive staged indices this step reads, counted from `base` (time-major kernel)
+      int64_t need = dmax + 1;
+      if (pmsm && plan.deadtime > 0 && ns > 0) {  // buffer leaves of saved state j read staged index j
+        const int64_t first = si - ns;
+        if (first < base) {
+          set_error("sim_ahead: a saved sample precedes the zero-order-hold index of its step");
+          return EXENV_ERR_UNSUPPORTED;
+        }
+        need = std::max<int64_t>(need, si - 1 - base + 1);
+      }
+      out.win_need = std::max(out.win_need, (int)need);
+    }
     out.words.push_back(w);
     out.dt.push_back((double)dt);
     save_count.push_back(ns);
@@ -203,6 +215,14 @@ static int upload_records(const ExenvPlan &plan, SimSchedule &s) {
   }
   std::vector<T> dt(s.dt.begin(), s.dt.end());
   dt.push_back((T)0);  // look-ahead padding (the kernel fetches step n+1 while integrating step n)
+  std::vector<StepRec<T>> steps(dt.size());
+  for (size_t i = 0; i < steps.size(); ++i) {
+    steps[i].w = i < s.words.size() ? s.words[i] : 0;
+    steps[i].dt = dt[i];
+    steps[i].pad = (T)0;
+  }
+  EX_CUDA(cudaMalloc(&s.d_steprec, steps.size() * sizeof(StepRec<T>)));
+  EX_CUDA(cudaMemcpy(s.d_steprec, steps.data(), steps.size() * sizeof(StepRec<T>), cudaMemcpyHostToDevice));
   EX_CUDA(cudaMalloc(&s.d_dt, dt.size() * sizeof(T)));
   EX_CUDA(cudaMalloc(&s.d_theta, recs.size() * sizeof(SaveRec<T>)));
   EX_CUDA(cudaMemcpy(s.d_dt, dt.data(), dt.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -225,6 +245,8 @@ static void free_schedule(SimSchedule &s) {
   cudaFree(s.d_dt);
   cudaFree(s.d_theta);
   cudaFree(s.d_tiles);
+  cudaFree(s.d_steprec);
+  s.d_steprec = nullptr;
   s.d_words = nullptr;
   s.d_dt = s.d_theta = nullptr;
   s.d_tiles = nullptr;
@@ -582,6 +604,10 @@ static int validate_sim(const ExenvPlan *plan, const ExenvSimArgs *a) {
     set_error("exenv_sim_ahead: actions/obs is NULL");
     return EXENV_ERR_NULL;
   }
+  if (a->layout != EXENV_LAYOUT_BATCH_MAJOR && a->layout != EXENV_LAYOUT_TIME_MAJOR) {
+    set_error("exenv_sim_ahead: unknown layout %d", a->layout);
+    return EXENV_ERR_INVALID;
+  }
   return EXENV_OK;
 }
 
@@ -616,6 +642,7 @@ int exenv_sim_ahead(exenv_plan_t plan, const ExenvSimArgs *a, void *stream) {
   if (rc != EXENV_OK) return rc;
   ExenvSimArgs b = *a;
   b.block_envs = E;
+  if (a->layout == EXENV_LAYOUT_TIME_MAJOR) return launch_simtm(*plan, b, *sch, (cudaStream_t)stream);
   return launch_sim(*plan, b, *sch, (cudaStream_t)stream);
 }
 
@@ -626,6 +653,10 @@ int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *h, int64_t chunk
   int rc = validate_sim(plan, h);
   if (rc != EXENV_OK) return rc;
   if (h->batch == 0) return EXENV_OK;
+  if (h->layout != EXENV_LAYOUT_BATCH_MAJOR) {
+    set_error("exenv_sim_ahead_host: host buffers are batch-major (the reference's layout)");
+    return EXENV_ERR_UNSUPPORTED;
+  }
   EX_CUDA(cudaSetDevice(plan->device));
   const size_t es = plan->desc.dtype == EXENV_F64 ? 8 : 4;
   const int D = plan->dims.n_phys, A = plan->dims.n_act, NODE = plan->dims.n_ode;

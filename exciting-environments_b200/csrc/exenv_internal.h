@@ -32,11 +32,13 @@ struct SimTile {
 struct SimSchedule {
   int64_t n_actions = 0, n_save = 0, n_steps = 0;
   int tile_steps = 0, n_tiles = 0, act_cap = 0, save_cap = 0;
+  int win_need = 1;  // time-major kernel: consecutive staged action indices a single solver step reads (from its base)
   // device copies
   uint64_t *d_words = nullptr;  // bits 0-31 min action index, 32-45 seven 2-bit stage deltas, 46-49 #saves
   void *d_dt = nullptr;         // T[n_steps]   tnext - tprev
   void *d_theta = nullptr;      // SaveRec<T>[n_save]  dense-output record of every save, in save order
   SimTile *d_tiles = nullptr;
+  void *d_steprec = nullptr;    // StepRec<T>[n_steps + 1]  packed (word, dt) for the time-major kernel
   // host copies (tests / shape queries)
   std::vector<uint64_t> words;
   std::vector<double> dt, theta;
@@ -75,6 +77,8 @@ int launch_epilogue_f32(const ExenvPlan &plan, const ExenvEpilogueArgs &a, cudaS
 int launch_epilogue_f64(const ExenvPlan &plan, const ExenvEpilogueArgs &a, cudaStream_t stream);
 int launch_sim_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_sim_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
+int launch_simtm_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
+int launch_simtm_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 size_t sim_smem_bytes_f32(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);
 size_t sim_smem_bytes_f64(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);
 
@@ -86,6 +90,9 @@ inline int launch_reset(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStre
 }
 inline int launch_sim(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t s) {
   return plan.desc.dtype == EXENV_F64 ? launch_sim_f64(plan, a, sch, s) : launch_sim_f32(plan, a, sch, s);
+}
+inline int launch_simtm(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t s) {
+  return plan.desc.dtype == EXENV_F64 ? launch_simtm_f64(plan, a, sch, s) : launch_simtm_f32(plan, a, sch, s);
 }
 // Shared-memory bytes the sim kernel needs for tiles of (step_cap steps, act_cap actions, save_cap saves).
 inline size_t sim_smem_bytes(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap) {

@@ -32,6 +32,26 @@ struct alignas(16) SaveRec {
   T v[8];
 };
 
+// Packed per-step schedule entry of the time-major kernel (one 16-byte load in fp32).
+template <typename T>
+struct alignas(16) StepRec {
+  uint64_t w;
+  T dt;
+  T pad;
+};
+
+// Action of stage `s` of the step described by word `w`.  A fetch object may provide stage(w, s, u) and decode the
+// 2-bit stage offset itself (time-major kernel: its window starts at the step's base index); plain callables
+// fetch(idx, u) receive the absolute zero-order-hold index.
+template <class F, typename T>
+EX_HD auto fetch_stage_(F &f, uint64_t w, int s, T *u, int) -> decltype(f.stage(w, s, u), void()) {
+  f.stage(w, s, u);
+}
+template <class F, typename T>
+EX_HD void fetch_stage_(F &f, uint64_t w, int s, T *u, long) {
+  f(sched_base(w) + sched_delta(w, s), u);
+}
+
 // Physical action for index `q` of the zero-order-hold sequence the solver sees.
 //  generic envs : denormalize_action of raw action q                               (core_env.py:468)
 //  PMSM         : q < deadtime -> the initial u_dq buffer; else raw action j = q - deadtime clipped to the voltage
@@ -115,7 +135,7 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
   T y1[NODE], k[7][NODE];
   if constexpr (SOLVER == EXENV_EULER) {  // diffrax.Euler
     T u[A], f0[NODE];
-    fetch(base + sched_delta(w, 0), u);
+    fetch_stage_(fetch, w, 0, u, 0);
     Env::template rhs<true>(y, u, p, pre, aux, f0);
 #pragma unroll
     for (int i = 0; i < NODE; ++i) {
@@ -128,7 +148,7 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
         y, f, dt,
         [&](int stage, const T *ys, T *fo) {
           T u[A];
-          fetch(base + sched_delta(w, stage), u);
+          fetch_stage_(fetch, w, stage, u, 0);
           Env::template rhs<true>(ys, u, p, pre, aux, fo);
         },
         y1, fl, k);
@@ -142,6 +162,7 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
     sim_save_one<Env, SOLVER, T>(rec0, y, y1, k, p, aux, save_idx, fetch, st);
     sink(save_idx, st);
     ++save_idx;
+#pragma unroll 1
     for (int q = 1; q < ns; ++q) {
       const SaveRec<T> rec = recs[save_idx];
       sim_save_one<Env, SOLVER, T>(rec, y, y1, k, p, aux, save_idx, fetch, st);
@@ -158,7 +179,7 @@ template <class Env, typename T, class Fetch>
 EX_HD void sim_first_derivative(uint64_t w0, const T *y, T *f, const T *p, const typename Env::Pre &pre,
                                 typename Env::Aux &aux, Fetch &&fetch) {
   T u[Env::A];
-  fetch(sched_base(w0) + sched_delta(w0, 0), u);
+  fetch_stage_(fetch, w0, 0, u, 0);
   Env::template rhs<true>(y, u, p, pre, aux, f);
 }
 

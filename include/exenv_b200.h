@@ -25,6 +25,10 @@
  *   - State leaves are structure-of-arrays: one (B,) array per PhysicalState field, in the reference's dataclass
  *     field order.  action (B, A), obs (B, O'), actions (B, T, A), observations (B, N+1, O'), trajectory leaves
  *     (B, N+1): C-contiguous, batch-major, exactly the reference's array shapes.  O' = O + n_control.
+ *     exenv_sim_ahead additionally offers EXENV_LAYOUT_TIME_MAJOR (structure of arrays over the batch: actions
+ *     (T, B, A), observations (N+1, B, O'), trajectory leaves (N+1, B), reward / terminated (N, B), truncated
+ *     (N+1, B, n_trunc)): the same logical arrays with the batch axis innermost, so that every warp access is one
+ *     contiguous segment.  The host mirror returns them as permuted views with the reference's shapes.
  *   - Outputs may alias the matching inputs leaf-by-leaf (each thread reads its element before writing it).
  *   - Kernels never allocate or retain caller pointers past the call; launches are asynchronous on `stream`
  *     (a cudaStream_t passed as void*), no host synchronisation, CUDA-graph capturable after the first call of a
@@ -42,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EXENV_ABI_VERSION 1
+#define EXENV_ABI_VERSION 2
 #define EXENV_MAX_PARAMS 32
 #define EXENV_MAX_CONTROL 8
 #define EXENV_MAX_PHYS 8
@@ -141,6 +145,12 @@ typedef struct ExenvStepArgs {
 int exenv_step(exenv_plan_t plan, const ExenvStepArgs *args, void *stream);
 
 /* ---- vmap_sim_ahead ------------------------------------------------------------------------------------------- */
+typedef enum ExenvLayout {
+  EXENV_LAYOUT_BATCH_MAJOR = 0, /* the reference's C-contiguous arrays: (B, T, A), (B, N+1, O'), (B, N+1) */
+  EXENV_LAYOUT_TIME_MAJOR = 1   /* batch axis innermost: (T, B, A), (N+1, B, O'), (N+1, B); reward/terminated (N, B),
+                                   truncated (N+1, B, n_trunc) */
+} ExenvLayout;
+
 typedef struct ExenvSimArgs {
   int64_t batch;
   int64_t n_actions;      /* T = actions.shape[1] */
@@ -159,13 +169,16 @@ typedef struct ExenvSimArgs {
   uint8_t *terminated; /* optional (B, N) */
   int32_t tile_steps;  /* solver steps staged per shared-memory tile; 0 = auto */
   int32_t block_envs;  /* reserved (the kernel uses 128 environments per CTA) */
+  int32_t layout;      /* ExenvLayout of actions / obs / traj / reward / truncated / terminated */
+  int32_t reserved_;
 } ExenvSimArgs;
 /* N+1 = 1 + int(action_stepsize * T / obs_stepsize) (pendulum_env.py:222-225) and the solver-step count of the
  * emulated diffeqsolve loop in the plan dtype. */
 int exenv_sim_ahead_shape(exenv_plan_t plan, int64_t n_actions, double obs_stepsize, double action_stepsize,
                           int64_t *n_save, int64_t *n_steps);
 int exenv_sim_ahead(exenv_plan_t plan, const ExenvSimArgs *args, void *stream);
-/* Same call with HOST buffers (pinned or pageable); chunk_envs environments per pipeline stage (0 = auto). */
+/* Same call with HOST buffers (pinned or pageable); chunk_envs environments per pipeline stage (0 = auto).
+ * Host buffers are always in the reference's batch-major layout (layout must be EXENV_LAYOUT_BATCH_MAJOR). */
 int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *host_args, int64_t chunk_envs);
 
 /* ---- reward / truncated / terminated of given states -------------------------------------------------------------

@@ -38,24 +38,46 @@ def horizon_tol(orc, st, acts, dtype, ref, scales):
     return max(HORIZON_TOL[dtype], 20 * sens), sens
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle_case(env, solver, dtype):
+    """Seeded inputs + oracle trajectories + tolerance of one (env, solver, dtype) case (shared by both layouts)."""
+    key = (env, solver, dtype)
+    if key not in _ORACLE_CACHE:
+        rng = np.random.default_rng(42)
+        orc = _orc(env, solver, dtype)
+        B, T = 300, 200  # 3 CTAs, the last one ragged
+        gentle = orc.env == "pmsm"
+        st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=gentle)
+        acts = rng.uniform(-1, 1, (B, T, orc.A)).astype(dtype)
+        if gentle:
+            acts *= 0.02
+        ref = orc.sim_ahead(st, acts, orc.tau, orc.tau, epilogue=True)
+        scales = field_scales(orc)
+        tol, sens = horizon_tol(orc, st, acts, dtype, ref, scales)
+        _ORACLE_CACHE.clear()  # keep one case alive: the two layouts of a case run back to back
+        _ORACLE_CACHE[key] = (orc, B, T, gentle, st, acts, ref, scales, tol, sens)
+    return _ORACLE_CACHE[key]
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("solver", [O.EULER, O.TSIT5])
 @pytest.mark.parametrize("env", ENVS + ["pmsm_brusa_sat", "pmsm_sew_sat"])
-def test_sim_ahead_matches_oracle(excenvs, env, solver, dtype):
-    rng = np.random.default_rng(42)
-    orc = _orc(env, solver, dtype)
-    B, T = 300, 200  # 3 CTAs, the last one ragged
-    gentle = orc.env == "pmsm"
-    st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=gentle)
-    acts = rng.uniform(-1, 1, (B, T, orc.A)).astype(dtype)
-    if gentle:
-        acts *= 0.02
-    ref = orc.sim_ahead(st, acts, orc.tau, orc.tau, epilogue=True)
+@pytest.mark.parametrize("layout,epilogue", [("batch_major", True), ("time_major", True), ("time_major", False)])
+def test_sim_ahead_matches_oracle(excenvs, env, solver, dtype, layout, epilogue):
+    """Both memory layouts (and, time-major, both the plain and the fused-epilogue instantiation) against the oracle."""
+    orc, B, T, gentle, st, acts, ref, scales, tol, sens = _oracle_case(env, solver, dtype)
     e = make_env(excenvs, orc, B)
-    obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(
-        to_state(e, st), torch.as_tensor(acts, device="cuda"), orc.tau, orc.tau)
-    scales = field_scales(orc)
-    tol, sens = horizon_tol(orc, st, acts, dtype, ref, scales)
+    a_dev = torch.as_tensor(acts, device="cuda")
+    if epilogue:
+        obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(
+            to_state(e, st), a_dev, orc.tau, orc.tau, layout=layout)
+    else:
+        obs, states, last = e.vmap_sim_ahead(to_state(e, st), a_dev, orc.tau, orc.tau, layout=layout)
+    if layout == "time_major":  # same logical shapes, batch axis innermost in memory
+        assert obs.permute(1, 0, 2).is_contiguous()
+        assert getattr(states.physical_state, e.PHYS_FIELDS[0]).t().is_contiguous()
     if gentle or orc.env in ("mass_spring_damper", "fluid_tank"):
         assert tol == HORIZON_TOL[dtype], ("scenario is unexpectedly ill-conditioned", sens)
     assert obs.shape == ref["obs"].shape
@@ -74,6 +96,8 @@ def test_sim_ahead_matches_oracle(excenvs, env, solver, dtype):
             s_ = scales[e.PHYS_FIELDS.index(n)]
             err = traj_err((np_(a) * orc.tau)[:, None], (np.asarray(b, np.float64) * orc.tau)[:, None], s_)
             assert err <= max(tol, 1e-5 if dtype == np.float32 else 1e-10) * 10, ("k_last", n, err)
+    if not epilogue:
+        return
     # flags: bit exact wherever the oracle's observation is not within rounding distance of the threshold
     tr_ref, tr = ref["truncated"], np_(trunc).astype(np.uint8)
     if orc.n_trunc == orc.O:
@@ -122,9 +146,11 @@ def test_tile_geometry_does_not_change_results(excenvs, tile_steps, block_envs):
     assert torch.equal(base[2].physical_state.omega, other[2].physical_state.omega)
 
 
+@pytest.mark.parametrize("layout", ["batch_major", "time_major"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("obs_dt,act_dt,T", [(5e-5, 1e-4, 64), (1e-4, 3e-4, 50), (2e-2, 2e-2, 300), (1e-3, 1e-3, 1)])
-def test_zoh_and_save_grid_quirks(excenvs, obs_dt, act_dt, T, dtype):
+@pytest.mark.parametrize("obs_dt,act_dt,T", [(5e-5, 1e-4, 64), (1e-4, 3e-4, 50), (2e-2, 2e-2, 300), (1e-3, 1e-3, 1),
+                                             (1e-4, 1e-4, 3000)])
+def test_zoh_and_save_grid_quirks(excenvs, obs_dt, act_dt, T, dtype, layout):
     """obs_stepsize < action_stepsize, coarse tau (ZOH lag), single action; time-varying actions."""
     rng = np.random.default_rng(11)
     orc = O.Oracle("mass_spring_damper", solver=O.TSIT5, dtype=dtype, tau=obs_dt)
@@ -133,13 +159,15 @@ def test_zoh_and_save_grid_quirks(excenvs, obs_dt, act_dt, T, dtype):
     acts = rng.uniform(-1, 1, (B, T, 1)).astype(dtype)
     ref = orc.sim_ahead(st, acts, obs_dt, act_dt)
     e = make_env(excenvs, orc, B)
-    obs, states, last = e.vmap_sim_ahead(to_state(e, st), torch.as_tensor(acts, device="cuda"), obs_dt, act_dt)
+    obs, states, last = e.vmap_sim_ahead(to_state(e, st), torch.as_tensor(acts, device="cuda"), obs_dt, act_dt,
+                                         layout=layout)
     assert obs.shape == ref["obs"].shape
     assert e.sim_ahead_shape(T, obs_dt, act_dt) == (ref["obs"].shape[1], ref["n_steps"])
     assert _cmp(np_(obs), ref["obs"], HORIZON_TOL[dtype])
 
 
-def test_reference_tracking_per_env_params_and_epilogue(excenvs):
+@pytest.mark.parametrize("layout", ["batch_major", "time_major"])
+def test_reference_tracking_per_env_params_and_epilogue(excenvs, layout):
     rng = np.random.default_rng(8)
     B, T = 200, 60
     base = O.Oracle("cart_pole", dtype=np.float32)
@@ -151,7 +179,7 @@ def test_reference_tracking_per_env_params_and_epilogue(excenvs):
     ref = orc.sim_ahead(st, acts, 1e-3, 1e-3, ref=refl, epilogue=True)
     e = make_env(excenvs, orc, B)
     obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(
-        to_state(e, st, refl), torch.as_tensor(acts, device="cuda"), 1e-3, 1e-3)
+        to_state(e, st, refl), torch.as_tensor(acts, device="cuda"), 1e-3, 1e-3, layout=layout)
     assert obs.shape == (B, T + 1, 6)
     assert _cmp(np_(obs), ref["obs"], 1e-4)
     assert _cmp(np_(rew)[..., 0], ref["reward"], 1e-3)
@@ -184,7 +212,8 @@ def test_euler_sim_ahead_equals_repeated_step(excenvs):
         assert np.allclose(np_(obs_a[:, -1]), np_(obs_s), rtol=1e-16, atol=1e-8), reg
 
 
-def test_full_size_linearity_property(excenvs):
+@pytest.mark.parametrize("layout", ["batch_major", "time_major"])
+def test_full_size_linearity_property(excenvs, layout):
     """BASELINE config 2 scale check with a size-independent property: the mass-spring-damper is linear, so the
     trajectory of (c*x0, c*u) is c times the trajectory of (x0, u) -- checked on 2^17 envs x 2000 Tsit5 steps."""
     B, T = 1 << 17, 2000
@@ -198,9 +227,9 @@ def test_full_size_linearity_property(excenvs):
     for s in (s1, s2):
         s.PRNGKey = nan
         s.reference = e.PhysicalState(nan, nan)
-    _, st1, _ = e.vmap_sim_ahead(s1, acts, 1e-4, 1e-4)
+    _, st1, _ = e.vmap_sim_ahead(s1, acts, 1e-4, 1e-4, layout=layout)
     # action normalisation is affine with zero offset (min = -max), so scaling the normalised action scales the force
-    _, st2, _ = e.vmap_sim_ahead(s2, 2 * acts, 1e-4, 1e-4)
+    _, st2, _ = e.vmap_sim_ahead(s2, 2 * acts, 1e-4, 1e-4, layout=layout)
     d = (st2.physical_state.deflection - 2 * st1.physical_state.deflection).abs().max().item()
     v = (st2.physical_state.velocity - 2 * st1.physical_state.velocity).abs().max().item()
     assert d < 1e-5 and v < 1e-4
@@ -260,3 +289,31 @@ def test_standalone_rew_trunc_term_ahead_equals_fused(excenvs, env, ctrl):
     # GymWrapper-style epilogue of a single batched state
     r1, tr1, te1 = e.vmap_generate_reward_truncated_terminated(last)
     assert torch.allclose(r1[:, 0], rew[:, -1, 0], rtol=1e-12, atol=1e-14) and torch.equal(tr1, trunc[:, -1])
+
+
+@pytest.mark.parametrize("env", ["mass_spring_damper", "pendulum", "cart_pole", "pmsm"])
+@pytest.mark.parametrize("solver", [O.EULER, O.TSIT5])
+def test_time_major_equals_batch_major(excenvs, env, solver):
+    """Both layouts run the same per-environment arithmetic (exenv_sim_core.cuh): the time-major views hold the same
+    values as the reference-contiguous arrays (to rounding: the two kernels are separate compilations), ragged batch,
+    zero-copy consumption of a time-major action view."""
+    rng = np.random.default_rng(17)
+    orc = O.Oracle(env, solver=solver, dtype=np.float32)
+    B, T = 1000 + 37, 96
+    gentle = env == "pmsm"
+    st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=gentle)
+    acts = rng.uniform(-1, 1, (B, T, orc.A)).astype(np.float32) * (0.02 if gentle else 1.0)
+    e = make_env(excenvs, orc, B)
+    a_bm = torch.as_tensor(acts, device="cuda")
+    a_tm = e.time_major_actions(T, fill=a_bm)
+    assert a_tm.shape == a_bm.shape and torch.equal(a_tm, a_bm) and a_tm.permute(1, 0, 2).is_contiguous()
+    o1, s1, l1 = e.vmap_sim_ahead(to_state(e, st), a_bm, orc.tau, orc.tau)
+    o2, s2, l2 = e.vmap_sim_ahead(to_state(e, st), a_tm, orc.tau, orc.tau, layout="time_major")
+    assert o1.shape == o2.shape and o1.is_contiguous() and not o2.is_contiguous()
+    scales = field_scales(orc)
+    for name, sc in zip(e.PHYS_FIELDS, scales):
+        x1, x2 = np_(getattr(s1.physical_state, name)), np_(getattr(s2.physical_state, name))
+        assert x1.shape == x2.shape == (B, T + 1)
+        assert traj_err(x2, x1, sc) <= 2e-6, name
+        assert np.array_equal(np_(getattr(l2.physical_state, name)), x2[:, -1])
+    assert np.max(np.abs(np_(o1) - np_(o2))) <= 1e-5

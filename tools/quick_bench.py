@@ -38,20 +38,26 @@ def bench_step(name, cls, solver, dtype, B):
                           env_steps_per_s=B / t, GBps=bytes_ / t / 1e9, frac_hbm=bytes_ / t / HBM)), flush=True)
 
 
-def bench_sim(name, cls, solver, dtype, B, T, tile_steps=0, block_envs=0, iters=3, **kw):
+def bench_sim(name, cls, solver, dtype, B, T, tile_steps=0, block_envs=0, iters=3, layout="batch_major", **kw):
     env = cls(batch_size=B, solver=solver, dtype=dtype, **kw)
     env.max_steps = None
     _, state = env.vmap_reset(rng=0)
     S = 4 if dtype == torch.float32 else 8
     D, A, O = env.physical_state_dim, env.action_dim, env.obs_dim
-    actions = torch.rand((B, T, A), device="cuda", dtype=dtype) * 2 - 1
-    obs = torch.empty((B, T + 1, O), device="cuda", dtype=dtype)
-    traj = [torch.empty((B, T + 1), device="cuda", dtype=dtype) for _ in range(D)]
+    tm = layout == "time_major"
+    if tm:
+        actions = (torch.rand((T, B, A), device="cuda", dtype=dtype) * 2 - 1).permute(1, 0, 2)
+        obs = torch.empty((T + 1, B, O), device="cuda", dtype=dtype)
+        traj = [torch.empty((T + 1, B), device="cuda", dtype=dtype) for _ in range(D)]
+    else:
+        actions = torch.rand((B, T, A), device="cuda", dtype=dtype) * 2 - 1
+        obs = torch.empty((B, T + 1, O), device="cuda", dtype=dtype)
+        traj = [torch.empty((B, T + 1), device="cuda", dtype=dtype) for _ in range(D)]
     out = dict(obs=obs, traj=traj)
     t = timed(lambda: env._sim_impl(env.env_properties, B, state, actions, env.tau, env.tau, tile_steps=tile_steps,
-                                    block_envs=block_envs, out=out), warm=2, iters=iters)
+                                    block_envs=block_envs, out=out, layout=layout), warm=2, iters=iters)
     bytes_ = S * (A + O + D) * B * T
-    print(json.dumps(dict(kind="sim", env=name, solver=repr(solver), dtype=str(dtype), B=B, T=T, tile=tile_steps,
+    print(json.dumps(dict(kind="sim", layout=layout, env=name, solver=repr(solver), dtype=str(dtype), B=B, T=T, tile=tile_steps,
                           block=block_envs, ms=t * 1e3, env_steps_per_s=B * T / t, GBps=bytes_ / t / 1e9,
                           frac_hbm=bytes_ / t / HBM)), flush=True)
     del obs, traj, actions
@@ -84,3 +90,20 @@ if __name__ == "__main__":
         bench_sim("pmsm", ex.PMSM, ex.Tsit5(), f32, 1 << 18, 1000, iters=2)
         bench_sim("pmsm_sat", ex.PMSM, ex.Tsit5(), f32, 1 << 17, 1000, iters=2, saturated=True,
                   motor_variant=ex.MotorVariant.BRUSA)
+    if what in ("all", "simtm"):
+        tm = dict(layout="time_major", iters=2)
+        bench_sim("msd", ex.MassSpringDamper, ex.Tsit5(), f32, 1 << 20, 2000, **tm)
+        bench_sim("msd", ex.MassSpringDamper, ex.Euler(), f32, 1 << 20, 2000, **tm)
+        bench_sim("msd", ex.MassSpringDamper, ex.Tsit5(), f64, 1 << 19, 2000, **tm)
+        bench_sim("msd", ex.MassSpringDamper, ex.Euler(), f64, 1 << 19, 2000, **tm)
+        bench_sim("tank", ex.FluidTank, ex.Tsit5(), f32, 1 << 20, 1000, **tm)
+        bench_sim("pendulum", ex.Pendulum, ex.Tsit5(), f32, 1 << 20, 1000, **tm)
+        bench_sim("pendulum", ex.Pendulum, ex.Euler(), f32, 1 << 20, 1000, **tm)
+        bench_sim("cartpole", ex.CartPole, ex.Tsit5(), f32, 1 << 22, 200, **tm)
+        bench_sim("cartpole", ex.CartPole, ex.Euler(), f32, 1 << 22, 200, **tm)
+        bench_sim("acrobot", ex.Acrobot, ex.Tsit5(), f32, 1 << 22, 200, **tm)
+        bench_sim("acrobot", ex.Acrobot, ex.Euler(), f32, 1 << 22, 200, **tm)
+        bench_sim("pmsm", ex.PMSM, ex.Tsit5(), f32, 1 << 18, 2500, **tm)
+        bench_sim("pmsm", ex.PMSM, ex.Euler(), f32, 1 << 18, 2500, **tm)
+        bench_sim("pmsm_sat", ex.PMSM, ex.Tsit5(), f32, 1 << 17, 2500, saturated=True,
+                  motor_variant=ex.MotorVariant.BRUSA, **tm)
