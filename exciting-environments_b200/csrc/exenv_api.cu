@@ -640,9 +640,9 @@ int exenv_sim_ahead(exenv_plan_t plan, const ExenvSimArgs *a, void *stream) {
   SimSchedule *sch = nullptr;
   rc = prepare_sim(plan, a, &E, &sch);
   if (rc != EXENV_OK) return rc;
+  if (a->layout == EXENV_LAYOUT_TIME_MAJOR) return launch_simtm(*plan, *a, *sch, (cudaStream_t)stream);
   ExenvSimArgs b = *a;
   b.block_envs = E;
-  if (a->layout == EXENV_LAYOUT_TIME_MAJOR) return launch_simtm(*plan, b, *sch, (cudaStream_t)stream);
   return launch_sim(*plan, b, *sch, (cudaStream_t)stream);
 }
 

@@ -58,7 +58,7 @@ struct SimTmK {
 
 __device__ __forceinline__ unsigned tm_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// Streaming (evict-first) vector access of BYTES = 4 / 8 / 16 bytes.
+// Streaming (evict-first) access of N consecutive scalars (N * sizeof(T) a power of two; 16-byte chunks at most).
 template <int BYTES>
 __device__ __forceinline__ void stcs_chunk(void *dst, const void *src) {
   if constexpr (BYTES == 16) {
@@ -75,36 +75,100 @@ __device__ __forceinline__ void stcs_chunk(void *dst, const void *src) {
     __stcs(reinterpret_cast<float *>(dst), t);
   }
 }
-template <int BYTES>
-__device__ __forceinline__ void ldcs_chunk(void *dst, const void *src) {
+// Loads are volatile asm: the kernel orders them by hand (see the solver loop) and ptxas must neither merge them into
+// wider accesses with dead lanes nor hoist the DRAM-latency action load above the schedule loads.
+template <int BYTES, bool NC>
+__device__ __forceinline__ void ld_chunk(void *dst, const void *src) {
   if constexpr (BYTES == 16) {
-    const float4 t = __ldcs(reinterpret_cast<const float4 *>(src));
+    uint4 t;
+    if constexpr (NC)
+      asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(src));
+    else
+      asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(src));
     memcpy(dst, &t, 16);
   } else if constexpr (BYTES == 8) {
-    const float2 t = __ldcs(reinterpret_cast<const float2 *>(src));
+    uint2 t;
+    if constexpr (NC)
+      asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(src));
+    else
+      asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(src));
     memcpy(dst, &t, 8);
   } else {
-    const float t = __ldcs(reinterpret_cast<const float *>(src));
+    unsigned t;
+    if constexpr (NC)
+      asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(t) : "l"(src));
+    else
+      asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(t) : "l"(src));
     memcpy(dst, &t, 4);
   }
 }
-
-// p + n elements with one IMAD.WIDE.U32 (running row pointers: the batch-axis stride fits 32 bits).
-template <typename P>
-__device__ __forceinline__ P *ptr_add(P *p, unsigned n) {
-  unsigned long long r;
-  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(n), "r"((unsigned)sizeof(P)), "l"((unsigned long long)p));
-  return reinterpret_cast<P *>(r);
+template <int BYTES>
+__device__ __forceinline__ void ldcs_chunk(void *dst, const void *src) {
+  ld_chunk<BYTES, false>(dst, src);
 }
-
-// O consecutive scalars with the widest vector stores (16 bytes at most).
-template <typename T, int O>
-__device__ __forceinline__ void store_row_vec(T *dst, const T *v) {
-  constexpr int ROW = O * (int)sizeof(T);
+// "these values are needed here": an empty volatile asm that consumes them, so that the scoreboard wait for their
+// loads sits at this point of the instruction stream (before the next volatile load is issued).
+__device__ __forceinline__ void consume_now(unsigned a) { asm volatile("" ::"r"(a)); }
+template <typename T, int N>
+__device__ __forceinline__ void store_vec(T *dst, const T *v) {
+  constexpr int ROW = N * (int)sizeof(T);
   constexpr int CH = ROW < 16 ? ROW : 16;
 #pragma unroll
   for (int i = 0; i < ROW / CH; ++i)
     stcs_chunk<CH>(reinterpret_cast<char *>(dst) + i * CH, reinterpret_cast<const char *>(v) + i * CH);
+}
+template <typename T, int N>
+__device__ __forceinline__ void load_vec(T *v, const T *src) {
+  constexpr int ROW = N * (int)sizeof(T);
+  constexpr int CH = ROW < 16 ? ROW : 16;
+#pragma unroll
+  for (int i = 0; i < ROW / CH; ++i)
+    ldcs_chunk<CH>(reinterpret_cast<char *>(v) + i * CH, reinterpret_cast<const char *>(src) + i * CH);
+}
+
+// Schedule entries are warp-uniform; explicit vector loads of exactly the fields the solver reads (a padded 128-bit
+// load would make the unused lane a write-after-write hazard for whatever the compiler puts there next).
+template <typename T>
+__device__ __forceinline__ StepRec<T> load_steprec(const StepRec<T> *p) {
+  StepRec<T> r;
+  uint4 q;
+  ld_chunk<16, true>(&q, p);
+  r.w = (uint64_t)q.x | ((uint64_t)q.y << 32);
+  if constexpr (sizeof(T) == 4) {
+    r.dt = __uint_as_float(q.z);
+    consume_now(q.z);
+  } else {
+    r.dt = __hiloint2double((int)q.w, (int)q.z);
+    consume_now(q.w);
+  }
+  r.pad = (T)0;
+  return r;
+}
+template <int SOLVER, typename T>
+__device__ __forceinline__ void load_saverec(SaveRec<T> &r, const SaveRec<T> *p) {
+  constexpr int N = SOLVER == EXENV_EULER ? 1 : 7;  // Euler: theta; Tsit5: seven dense-output weights
+  constexpr int BYTES = N * (int)sizeof(T);
+  char *dst = reinterpret_cast<char *>(r.v);
+  const char *src = reinterpret_cast<const char *>(p->v);
+  int off = 0;
+#pragma unroll
+  for (int ch = 16; ch >= 4; ch >>= 1) {
+#pragma unroll
+    for (int rep = 0; rep < 4; ++rep) {
+      if (off + ch <= BYTES) {
+        if (ch == 16) ld_chunk<16, true>(dst + off, src + off);
+        else if (ch == 8) ld_chunk<8, true>(dst + off, src + off);
+        else ld_chunk<4, true>(dst + off, src + off);
+        off += ch;
+      }
+    }
+  }
+  unsigned last_word;
+  memcpy(&last_word, dst + BYTES - 4, 4);
+  consume_now(last_word);
+  unsigned first_word;
+  memcpy(&first_word, dst, 4);
+  consume_now(first_word);
 }
 
 // The window of prepared actions as the `fetch` object of exenv_sim_core.cuh.  Slot 0 holds the step's base index
@@ -129,19 +193,60 @@ struct TmFetch {
   __device__ __forceinline__ void operator()(int idx, T *u) const { pick(idx - wbase, u); }
 };
 
-// GENERIC: reference entries in the observation (control_state != []), the fused reward / truncated / terminated
-// outputs (vmap_generate_rew_trunc_term_ahead, core_env.py:618-647) or per-environment parameters.
-template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W>
+// The same window for a step whose stages read at most two consecutive indices (every step, up to the rare lag of
+// the accumulated solver time): one select per stage on the low offset bit.
+template <typename T, int A, int W>
+struct TmFetchPair {
+  const TmFetch<T, A, W> &f;
+  __device__ __forceinline__ void stage(uint64_t w, int s, T *u) const {
+    const bool hi = (unsigned)(w >> (32 + 2 * s)) & 1u;
+#pragma unroll
+    for (int c = 0; c < A; ++c) u[c] = hi ? f.uw[1][c] : f.uw[0][c];
+  }
+  __device__ __forceinline__ void operator()(int idx, T *u) const { f(idx, u); }
+};
+
+// Light right-hand sides carry a second copy of the step body for such steps (W = 4 windows only).
+template <class Env>
+constexpr bool simtm_dual_path() {
+  return Env::ID == 0 || Env::ID == 1 || Env::ID == 2;
+}
+
+// PhysicalState fields of a saved sample from its staged values (PMSM: eps, i_d, i_q, torque, u_d_buffer, u_q_buffer).
+template <class Env, typename T>
+__device__ __forceinline__ void staged_to_fields(const T *st, T omega_el, T *sv) {
+  if constexpr (Env::IS_PMSM) {
+    sv[0] = st[4];
+    sv[1] = st[5];
+    sv[2] = st[0];
+    sv[3] = st[1];
+    sv[4] = st[2];
+    sv[5] = st[3];
+    sv[6] = omega_el;
+  } else {
+#pragma unroll
+    for (int d = 0; d < Env::D; ++d) sv[d] = st[d];
+  }
+}
+
+// V consecutive environments per thread: their leaves / action rows / observation rows are moved with one vector
+// access each, and the per-step bookkeeping (schedule fetch and decode, window slide, pointer updates, loop) is paid
+// once for V env-steps.  V > 1 needs B % V == 0 and V * sizeof(T)-aligned buffers (the launcher checks).
+// GENERIC (V == 1 only): reference entries in the observation (control_state != []), the fused reward / truncated /
+// terminated outputs (vmap_generate_rew_trunc_term_ahead, core_env.py:618-647), per-environment parameters, skipped
+// (NULL) trajectory leaves.
+template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V>
 __global__ void __launch_bounds__(SIMTM_THREADS)
     simtm_kernel(const __grid_constant__ SimTmK<T> a, const __grid_constant__ KParams<T> kp) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
   constexpr int NST = staged_values<Env>();
+  static_assert(!GENERIC || V == 1, "the generic instantiation handles one environment per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;  // first environment of this thread
   const bool valid = b < a.B;
 
-  typename Env::Aux aux{};
+  typename Env::Aux aux[V];
   if constexpr (Env::IS_PMSM && Env::SATURATED) {
     // stage the flux maps once per CTA: TMA bulk copy + mbarrier (SASS: UBLKCP)
     unsigned char *sm_lut = smem_raw;
@@ -165,13 +270,16 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
           : "r"(tm_smem_u32(mbar))
           : "memory");
     }
-    aux.lut.gx = reinterpret_cast<const T *>(sm_lut);
-    aux.lut.gy = reinterpret_cast<const T *>(sm_lut + a.lut_off_gy);
-    aux.lut.cells = reinterpret_cast<const T *>(sm_lut + a.lut_off_cells);
-    aux.lut.nx = a.lut_nx;
-    aux.lut.ny = a.lut_ny;
-    aux.lut.inv_dx = a.lut_inv_dx;
-    aux.lut.inv_dy = a.lut_inv_dy;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      aux[v].lut.gx = reinterpret_cast<const T *>(sm_lut);
+      aux[v].lut.gy = reinterpret_cast<const T *>(sm_lut + a.lut_off_gy);
+      aux[v].lut.cells = reinterpret_cast<const T *>(sm_lut + a.lut_off_cells);
+      aux[v].lut.nx = a.lut_nx;
+      aux[v].lut.ny = a.lut_ny;
+      aux[v].lut.inv_dx = a.lut_inv_dx;
+      aux[v].lut.inv_dy = a.lut_inv_dy;
+    }
   }
   if (!valid) return;  // no block-wide synchronisation below
 
@@ -184,32 +292,40 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   }
   const typename Env::Pre pre = Env::precompute(p);
   const T *pn = p + Env::NSTATIC;
-  T s0[D];
+  T s0[V][D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) s0[d] = __ldg(a.sin[d] + b);
-  T y[NODE], f[NODE];
-  if constexpr (Env::IS_PMSM) {
-    y[0] = s0[3];
-    y[1] = s0[4];
-    y[2] = s0[2];
-    aux.omega_el = s0[6];
-    aux.deadtime = a.deadtime;
-  } else {
+  for (int d = 0; d < D; ++d) {
+    T tmp[V];
+    load_vec<T, V>(tmp, a.sin[d] + b);
 #pragma unroll
-    for (int i = 0; i < NODE; ++i) y[i] = s0[i];
+    for (int v = 0; v < V; ++v) s0[v][d] = tmp[v];
   }
+  T y[V][NODE], f[V][NODE], last[V][NST];
 #pragma unroll
-  for (int i = 0; i < NODE; ++i) f[i] = (T)0;
-  T last[NST];
+  for (int v = 0; v < V; ++v) {
+    if constexpr (Env::IS_PMSM) {
+      y[v][0] = s0[v][3];
+      y[v][1] = s0[v][4];
+      y[v][2] = s0[v][2];
+      aux[v].omega_el = s0[v][6];
+      aux[v].deadtime = a.deadtime;
+    } else {
 #pragma unroll
-  for (int i = 0; i < NST; ++i) last[i] = (T)0;
+      for (int i = 0; i < NODE; ++i) y[v][i] = s0[v][i];
+    }
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) f[v][i] = (T)0;
+#pragma unroll
+    for (int i = 0; i < NST; ++i) last[v][i] = (T)0;
+  }
 
   // observation normalisation: prepared reciprocal of every span (correctly rounded quotient, exenv_math.cuh)
   InvDiv<T> sdiv[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<T>(pn[2 * d + 1] - pn[2 * d]);
-  T om_norm = (T)0;
-  if constexpr (Env::IS_PMSM) om_norm = norm_inv<true, T>(s0[6], pn[12], sdiv[6]);
+  T om_norm[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) om_norm[v] = Env::IS_PMSM ? norm_inv<true, T>(s0[v][D - 1], pn[2 * (D - 1)], sdiv[D - 1]) : (T)0;
   T rf[D];
   if constexpr (GENERIC) {
 #pragma unroll
@@ -221,132 +337,163 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   // ---- window of prepared ZOH actions: uw[k] = physical action of staged index wbase + k, k < W -------------------
   // Slot 0 follows the step's smallest stage index (`base`); the window slides by whole entries, the new last entry
   // is prepared from a raw action whose load was issued one slide earlier (>= one solver step of latency hiding).
-  // Every staged index is loaded and prepared exactly once.
+  // Every staged index is loaded and prepared exactly once.  Staged indices are loaded strictly in order: ap points
+  // at the raw action of the next one (staged q -> raw action q - dead; the PMSM buffer entry q < dead carries no
+  // load; past the end the last action is re-read, never used).
   const int dead = Env::IS_PMSM ? a.deadtime : 0;
   const int q_max = (int)a.n_actions - 1 + dead;  // last staged index that exists
-  TmFetch<T, A, W> win;
-  T pend[A];
-  win.wbase = 0;
-  // staged indices are loaded strictly in order: ap points at the raw action of the next one (staged q -> raw action
-  // q - dead; the PMSM buffer entry q < dead carries no load; past the end the last action is re-read, never used)
+  TmFetch<T, A, W> win[V];
+  T pend[V][A];
+  int wbase = 0;
   const T *ap = a.actions + b * A;
   int qn = 0;
   const unsigned act_stride = (unsigned)(a.B * A);
-  auto load_next = [&](T *raw) {
+  constexpr int PF_AHEAD = 6;  // solver steps between the L2 prefetch of an action row segment and its load
+  auto load_next = [&](T (*raw)[A]) {
     if (!Env::IS_PMSM || qn >= dead) {
-      ldcs_chunk<A * (int)sizeof(T)>(raw, ap);
-      if (qn < q_max) ap = ptr_add(ap, act_stride);
+      load_vec<T, V * A>(&raw[0][0], ap);
+      // the segment this thread will load PF_AHEAD slides from now starts its trip from DRAM to L2 here (no register,
+      // no scoreboard entry), so the load above finds its data in L2
+      if (qn + PF_AHEAD <= q_max)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)PF_AHEAD * act_stride));
+      if (qn < q_max) ap += act_stride;
     } else {
 #pragma unroll
-      for (int c = 0; c < A; ++c) raw[c] = (T)0;
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int c = 0; c < A; ++c) raw[v][c] = (T)0;
     }
     ++qn;
   };
-  auto prepare = [&](int q, const T *raw, T *u) {
+  auto prepare = [&](int q, const T (*raw)[A], int k) {
     q = q < q_max ? q : q_max;
-    prepare_action<Env, T>((long)q, raw, s0, p, a.deadtime, a.n_actions, a.pmsm_adv, a.pmsm_lin_stop, u);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      prepare_action<Env, T>((long)q, raw[v], s0[v], p, a.deadtime, a.n_actions, a.pmsm_adv, a.pmsm_lin_stop,
+                             win[v].uw[k]);
   };
 #pragma unroll
   for (int k = 0; k < W; ++k) {
-    T raw[A];
+    T raw[V][A];
     load_next(raw);
-    prepare(k, raw, win.uw[k]);
+    prepare(k, raw, k);
   }
   load_next(pend);
+  bool pend_valid = true;  // `pend` holds the raw action of staged index wbase + W
   auto slide_to = [&](int base) {
 #pragma unroll 1
-    while (win.wbase < base) {
+    while (wbase < base) {
+      if (!pend_valid) load_next(pend);  // only when one step slides the window by more than one entry
 #pragma unroll
-      for (int k = 0; k + 1 < W; ++k)
+      for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int c = 0; c < A; ++c) win.uw[k][c] = win.uw[k + 1][c];
-      ++win.wbase;
-      prepare(win.wbase + W - 1, pend, win.uw[W - 1]);
-      load_next(pend);
+        for (int k = 0; k + 1 < W; ++k)
+#pragma unroll
+          for (int c = 0; c < A; ++c) win[v].uw[k][c] = win[v].uw[k + 1][c];
+      ++wbase;
+      prepare(wbase + W - 1, pend, W - 1);
+      pend_valid = false;
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) win[v].wbase = wbase;
   };
 
-  // ---- save sink: saves arrive in order (0, 1, 2, ...), so every output keeps a running per-thread pointer ---------
+  // ---- saves ------------------------------------------------------------------------------------------------------
+  // Fast path: the first save of a step (the only one, except for the step that also saves ts[0]) is stashed per
+  // environment and written after all V environments of the thread have stepped: one vector store per trajectory
+  // leaf and per observation row group, through running row pointers.  Further saves of the same step and the
+  // GENERIC instantiation store element-wise.
   const unsigned Bu = (unsigned)a.B;
   T *tp[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) tp[d] = a.traj[d] ? a.traj[d] + b : nullptr;
   T *op = a.obs + b * OW;
-  T *rwp = (GENERIC && a.reward) ? a.reward + b : nullptr;
-  uint8_t *trp = (GENERIC && a.trunc) ? a.trunc + b * nt : nullptr;
-  uint8_t *tmp = (GENERIC && a.term) ? a.term + b : nullptr;
-  auto sink = [&](long sidx, const T *st) {
-#pragma unroll
-    for (int i = 0; i < NST; ++i) last[i] = st[i];
-    T sv[D];
+  T stash[V][NST];
+  long step_first_save = 0;  // save index the running pointers address
+  auto obs_fast = [&](int v, const T *st, const T *sv, T *ob) {
     if constexpr (Env::IS_PMSM) {
-      sv[0] = st[4];
-      sv[1] = st[5];
-      sv[2] = st[0];
-      sv[3] = st[1];
-      sv[4] = st[2];
-      sv[5] = st[3];
-      sv[6] = s0[6];
+      ob[0] = norm_inv<true, T>(sv[3], pn[6], sdiv[3]);
+      ob[1] = norm_inv<true, T>(sv[4], pn[8], sdiv[4]);
+      ob[2] = om_norm[v];
+      ob[3] = norm_inv<true, T>(sv[5], pn[10], sdiv[5]);
+      ob[4] = st[6];
+      ob[5] = st[7];
+      ob[6] = norm_inv<true, T>(sv[0], pn[0], sdiv[0]);
+      ob[7] = norm_inv<true, T>(sv[1], pn[2], sdiv[1]);
     } else {
 #pragma unroll
-      for (int d = 0; d < D; ++d) sv[d] = st[d];
+      for (int o = 0; o < O; ++o) ob[o] = norm_inv<true, T>(sv[o], pn[2 * o], sdiv[o]);
     }
+  };
+  auto sink_v = [&](int v, long sidx, const T *st) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if (!GENERIC || tp[d]) {
-        __stcs(tp[d], sv[d]);
-        tp[d] = ptr_add(tp[d], Bu);
-      }
-    }
+    for (int i = 0; i < NST; ++i) last[v][i] = st[i];
     if constexpr (!GENERIC) {
-      T ob[O];
-      if constexpr (Env::IS_PMSM) {
-        ob[0] = norm_inv<true, T>(sv[3], pn[6], sdiv[3]);
-        ob[1] = norm_inv<true, T>(sv[4], pn[8], sdiv[4]);
-        ob[2] = om_norm;
-        ob[3] = norm_inv<true, T>(sv[5], pn[10], sdiv[5]);
-        ob[4] = st[6];
-        ob[5] = st[7];
-        ob[6] = norm_inv<true, T>(sv[0], pn[0], sdiv[0]);
-        ob[7] = norm_inv<true, T>(sv[1], pn[2], sdiv[1]);
-      } else {
+      if (sidx == step_first_save) {
 #pragma unroll
-        for (int o = 0; o < O; ++o) ob[o] = norm_inv<true, T>(sv[o], pn[2 * o], sdiv[o]);
+        for (int i = 0; i < NST; ++i) stash[v][i] = st[i];
+      } else {  // rare: a later save of the same step
+        const size_t roff = (size_t)(sidx - step_first_save) * Bu + v;
+        T sv[D], ob[O];
+        staged_to_fields<Env, T>(st, s0[v][D - 1], sv);
+#pragma unroll
+        for (int d = 0; d < D; ++d) __stcs(tp[d] + roff, sv[d]);
+        obs_fast(v, st, sv, ob);
+#pragma unroll
+        for (int o = 0; o < O; ++o) __stcs(op + roff * O + o, ob[o]);
       }
-      store_row_vec<T, O>(op, ob);
-      op = ptr_add(op, Bu * (unsigned)O);
     } else {
+      const size_t row = (size_t)sidx * Bu + b;
+      T sv[D];
+      staged_to_fields<Env, T>(st, s0[0][D - 1], sv);
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        if (a.traj[d]) __stcs(a.traj[d] + row, sv[d]);
       T ob[O + EXENV_MAX_CONTROL];
       observe<Env, T>(sv, p, ob);
 #pragma unroll
       for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
         if (j < a.n_control) ob[O + j] = norm_field<Env, T>(a.control[j], rf, p);
+      T *dst = a.obs + row * OW;
 #pragma unroll
       for (int o = 0; o < O + EXENV_MAX_CONTROL; ++o)
-        if (o < OW) __stcs(op + o, ob[o]);
-      op += (size_t)Bu * (unsigned)OW;
-      if (rwp || trp || tmp) {
+        if (o < OW) __stcs(dst + o, ob[o]);
+      if (a.reward || a.trunc || a.term) {
         bool t0 = false;
 #pragma unroll
         for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
           if (i < nt) {
             const bool tv = trunc_entry<Env, T>(i, sv, ob, p);
             if (i == 0) t0 = tv;
-            if (trp) trp[i] = tv;
+            if (a.trunc) a.trunc[row * nt + i] = tv;
           }
-        if (trp) trp += (size_t)Bu * (unsigned)nt;
         if (sidx >= 1) {
           const T rw = a.n_control > 0 ? reward_of<Env, T>(sv, rf, p, a.n_control, a.control) : (T)0;
-          if (rwp) {
-            __stcs(rwp, rw);
-            rwp += Bu;
-          }
-          if (tmp) {
-            *tmp = terminated_of<Env, T>(rw, t0);
-            tmp += Bu;
-          }
+          const size_t r1 = row - Bu;
+          if (a.reward) __stcs(a.reward + r1, rw);
+          if (a.term) a.term[r1] = terminated_of<Env, T>(rw, t0);
         }
       }
+    }
+  };
+  auto flush = [&](int ns) {  // vector stores of the stashed first save, then the row pointers move on by ns saves
+    if constexpr (!GENERIC) {
+      T sv[V][D], ob[V][O];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        staged_to_fields<Env, T>(stash[v], s0[v][D - 1], sv[v]);
+        obs_fast(v, stash[v], sv[v], ob[v]);
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        T col[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) col[v] = sv[v][d];
+        store_vec<T, V>(tp[d], col);
+        tp[d] += (size_t)Bu * (unsigned)ns;
+      }
+      store_vec<T, V * O>(op, &ob[0][0]);
+      op += (size_t)Bu * (unsigned)(ns * O);
     }
   };
 
@@ -354,59 +501,97 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   // output record of a step is only needed after its last stage, so its load is issued at the top of the same step
   long save_idx = 0;
   const StepRec<T> *sp = a.steps;
-  StepRec<T> s_next = *sp;
+  StepRec<T> s_next = load_steprec<T>(sp);
   slide_to(sched_base(s_next.w));
-  if constexpr (SOLVER == EXENV_TSIT5) sim_first_derivative<Env, T>(s_next.w, y, f, p, pre, aux, win);
+  if constexpr (SOLVER == EXENV_TSIT5) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) sim_first_derivative<Env, T>(s_next.w, y[v], f[v], p, pre, aux[v], win[v]);
+  }
   const int n_steps = (int)a.n_steps;
 #pragma unroll 1
   for (int i = 0; i < n_steps; ++i) {
     const uint64_t w = s_next.w;
     const T dt = s_next.dt;
-    const SaveRec<T> rec = a.recs[save_idx];
-    s_next = *++sp;  // one look-ahead entry is appended by the host
+    // Load order at the top of a step (all volatile asm, so it is kept): the window slide consumes the action that
+    // left for DRAM one step ago; the warp-uniform schedule entries (L1 hits) are loaded and waited for; only then
+    // is the next action load issued, so that no scoreboard wait inside the step sits behind a DRAM access.
     slide_to(sched_base(w));
-    sim_one_step<Env, SOLVER, T>(w, dt, y, f, p, pre, aux, rec, a.recs, save_idx, win, sink);
-  }
-  // ---- last_state (core_env.py:484-488) and the fresh solver.init derivative at (t1, y_last) --------------------
-  T sl[D];
-  if constexpr (Env::IS_PMSM) {
-    sl[0] = last[4];
-    sl[1] = last[5];
-    sl[2] = last[0];
-    sl[3] = last[1];
-    sl[4] = last[2];
-    sl[5] = last[3];
-    sl[6] = s0[6];
-  } else {
+    SaveRec<T> rec;
+    load_saverec<SOLVER, T>(rec, a.recs + save_idx);
+    s_next = load_steprec<T>(++sp);  // one look-ahead entry is appended by the host
+    if (!pend_valid) {
+      load_next(pend);
+      pend_valid = true;
+    }
+    step_first_save = save_idx;
+    long si = save_idx;
+    if (W > 2 && SOLVER == EXENV_TSIT5 && simtm_dual_path<Env>() && sched_dmax(w) <= 1) {
 #pragma unroll
-    for (int i = 0; i < NODE; ++i) sl[i] = last[i];
+      for (int v = 0; v < V; ++v) {
+        si = save_idx;
+        const TmFetchPair<T, A, W> pair{win[v]};
+        sim_one_step<Env, SOLVER, T>(w, dt, y[v], f[v], p, pre, aux[v], rec, a.recs, si, pair,
+                                     [&](long sidx, const T *st) { sink_v(v, sidx, st); });
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        si = save_idx;
+        sim_one_step<Env, SOLVER, T>(w, dt, y[v], f[v], p, pre, aux[v], rec, a.recs, si, win[v],
+                                     [&](long sidx, const T *st) { sink_v(v, sidx, st); });
+      }
+    }
+    const int ns = sched_saves(w);
+    if (ns > 0) flush(ns);
+    save_idx = si;
+  }
+
+  // ---- last_state (core_env.py:484-488) and the fresh solver.init derivative at (t1, y_last) --------------------
+  const int q_last = (int)(a.n_actions - 1);
+  const bool want_k = SOLVER == EXENV_TSIT5 && a.klast[0];
+  if (want_k && q_last > wbase + W - 1) slide_to(q_last - (W - 1));
+  (void)pend_valid;
+  T sl[V][D], fi[V][NODE];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    staged_to_fields<Env, T>(last[v], s0[v][D - 1], sl[v]);
+    if (want_k) {
+      // solver.init(term, t1, t1 + tau, y_last, args): derivative with the ZOH closure at t1 -> clamped last action
+      T u[A], yl[NODE];
+      win[v](q_last, u);
+      if constexpr (Env::IS_PMSM) {
+        yl[0] = last[v][1];
+        yl[1] = last[v][2];
+        yl[2] = last[v][0];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NODE; ++i) yl[i] = last[v][i];
+      }
+      Env::template rhs<true>(yl, u, p, pre, aux[v], fi[v]);
+    }
   }
 #pragma unroll
   for (int d = 0; d < D; ++d)
-    if (a.last[d]) a.last[d][b] = sl[d];
-  if (SOLVER == EXENV_TSIT5 && a.klast[0]) {
-    // solver.init(term, t1, t1 + tau, y_last, args): derivative with the ZOH closure at t1 -> clamped last action
-    const int q = (int)(a.n_actions - 1);
-    if (q > win.wbase + W - 1) slide_to(q - (W - 1));
-    T u[A], yl[NODE], fi[NODE];
-    win(q, u);
-    if constexpr (Env::IS_PMSM) {
-      yl[0] = last[1];
-      yl[1] = last[2];
-      yl[2] = last[0];
-    } else {
+    if (a.last[d]) {
+      T col[V];
 #pragma unroll
-      for (int i = 0; i < NODE; ++i) yl[i] = last[i];
+      for (int v = 0; v < V; ++v) col[v] = sl[v][d];
+      store_vec<T, V>(a.last[d] + b, col);
     }
-    Env::template rhs<true>(yl, u, p, pre, aux, fi);
+  if (want_k) {
 #pragma unroll
-    for (int i = 0; i < NODE; ++i) a.klast[i][b] = fi[i];
+    for (int i = 0; i < NODE; ++i) {
+      T col[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) col[v] = fi[v][i];
+      store_vec<T, V>(a.klast[i] + b, col);
+    }
   }
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------------------
-template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W>
-static int launch_simtm_w(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V>
+static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
   SimTmK<T> a{};
   a.B = x.batch;
   a.n_actions = x.n_actions;
@@ -439,14 +624,10 @@ static int launch_simtm_w(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   a.lut_ny = plan.lut.ny;
   a.lut_inv_dx = (T)plan.lut.inv_dx;
   a.lut_inv_dy = (T)plan.lut.inv_dy;
-  if (Env::A == 2 && reinterpret_cast<uintptr_t>(x.actions) % (2 * sizeof(T)) != 0) {
-    set_error("exenv_sim_ahead (time-major): actions must be aligned to %zu bytes", 2 * sizeof(T));
-    return EXENV_ERR_ALIGN;
-  }
   KParams<T> kp = make_kparams<T>(plan);
   size_t smem = 0;
   if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = plan.lut.bytes + 16;
-  auto kern = simtm_kernel<Env, SOLVER, T, PER_ENV, GENERIC, W>;
+  auto kern = simtm_kernel<Env, SOLVER, T, PER_ENV, GENERIC, W, V>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -454,7 +635,8 @@ static int launch_simtm_w(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
       return EXENV_ERR_CUDA;
     }
   }
-  const unsigned grid = (unsigned)((x.batch + SIMTM_THREADS - 1) / SIMTM_THREADS);
+  const long threads = (x.batch + V - 1) / V;
+  const unsigned grid = (unsigned)((threads + SIMTM_THREADS - 1) / SIMTM_THREADS);
   kern<<<grid, SIMTM_THREADS, smem, stream>>>(a, kp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
@@ -467,12 +649,51 @@ static int launch_simtm_w(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
 
 // Window length: 2 covers every schedule whose steps read at most two consecutive ZOH indices (always the case up to
 // floating-point lag of the accumulated solver time); 4 is the general case (build_schedule_t rejects more).
-template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC>
-static int launch_simtm_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
-  if (sch.win_need <= 2) return launch_simtm_w<Env, SOLVER, T, PER_ENV, GENERIC, 2>(plan, x, sch, stream);
-  if (sch.win_need <= 4) return launch_simtm_w<Env, SOLVER, T, PER_ENV, GENERIC, 4>(plan, x, sch, stream);
+template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int V>
+static int launch_simtm_w(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+  if (sch.win_need <= 2) return launch_simtm_v<Env, SOLVER, T, PER_ENV, GENERIC, 2, V>(plan, x, sch, stream);
+  if (sch.win_need <= 4) return launch_simtm_v<Env, SOLVER, T, PER_ENV, GENERIC, 4, V>(plan, x, sch, stream);
   set_error("sim_ahead (time-major): a solver step needs %d consecutive actions (> 4)", sch.win_need);
   return EXENV_ERR_UNSUPPORTED;
+}
+
+// Environments per thread of the fast instantiation (tools/quick_bench.py simtm sweep on B200, profiles/README.md):
+// light right-hand sides gain from sharing the per-step bookkeeping between more environments; heavy ones (acrobot,
+// saturated PMSM) are bound by their own arithmetic and registers.
+template <class Env, int SOLVER, typename T>
+constexpr int simtm_auto_v() {
+  if (Env::ID == 4) return SOLVER == EXENV_TSIT5 ? 1 : 2;
+  if (Env::IS_PMSM) return Env::SATURATED ? 1 : 2;
+  if (Env::ID == 3) return 2;
+  return sizeof(T) == 4 ? 4 : 2;
+}
+
+template <class Env, int SOLVER, typename T>
+static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+  constexpr int VMAX = Env::IS_PMSM ? 2 : 4;  // instantiated widths: 1, 2, (4)
+  int v = x.block_envs > 0 ? x.block_envs : simtm_auto_v<Env, SOLVER, T>();
+  if (v > VMAX) v = VMAX;
+  if (v == 3) v = 2;
+  // V consecutive environments per thread move as one vector: the batch must split evenly and every buffer must be
+  // aligned to the vector (at most 16 bytes per access)
+  auto ok = [&](int vv) {
+    if (vv == 1) return true;
+    if (x.batch % vv) return false;
+    const size_t leaf = std::min<size_t>(16, (size_t)vv * sizeof(T));
+    const size_t arow = std::min<size_t>(16, (size_t)vv * Env::A * sizeof(T));
+    const size_t orow = std::min<size_t>(16, (size_t)vv * Env::O * sizeof(T));
+    auto al = [](const void *p, size_t n) { return reinterpret_cast<uintptr_t>(p) % n == 0; };
+    bool r = al(x.actions, arow) && al(x.obs, orow);
+    for (int d = 0; d < Env::D; ++d) r = r && al(x.state_in[d], leaf) && al(x.traj[d], leaf) && al(x.last[d], leaf);
+    for (int d = 0; d < Env::NODE; ++d) r = r && al(x.k_last[d], leaf);
+    return r;
+  };
+  while (v > 1 && !ok(v)) v >>= 1;
+  if constexpr (VMAX >= 4) {
+    if (v == 4) return launch_simtm_w<Env, SOLVER, T, false, false, 4>(plan, x, sch, stream);
+  }
+  if (v == 2) return launch_simtm_w<Env, SOLVER, T, false, false, 2>(plan, x, sch, stream);
+  return launch_simtm_w<Env, SOLVER, T, false, false, 1>(plan, x, sch, stream);
 }
 
 template <class Env, typename T>
@@ -486,23 +707,17 @@ static int simtm_dispatch2(const ExenvPlan &plan, const ExenvSimArgs &x, const S
     const size_t row_bytes = (size_t)Env::O * sizeof(T);
     const size_t vec = row_bytes < 16 ? row_bytes : 16;
     generic |= reinterpret_cast<uintptr_t>(x.obs) % vec != 0;
+    generic |= reinterpret_cast<uintptr_t>(x.actions) % ((size_t)Env::A * sizeof(T)) != 0;
   }
-  if constexpr (Env::IS_PMSM) {
-    if (generic)
-      return tsit ? launch_simtm_t<Env, EXENV_TSIT5, T, false, true>(plan, x, s, st)
-                  : launch_simtm_t<Env, EXENV_EULER, T, false, true>(plan, x, s, st);
-    return tsit ? launch_simtm_t<Env, EXENV_TSIT5, T, false, false>(plan, x, s, st)
-                : launch_simtm_t<Env, EXENV_EULER, T, false, false>(plan, x, s, st);
-  } else {
+  if constexpr (!Env::IS_PMSM) {
     if (plan.per_env)  // per-environment parameters always take the generic instantiation
-      return tsit ? launch_simtm_t<Env, EXENV_TSIT5, T, true, true>(plan, x, s, st)
-                  : launch_simtm_t<Env, EXENV_EULER, T, true, true>(plan, x, s, st);
-    if (generic)
-      return tsit ? launch_simtm_t<Env, EXENV_TSIT5, T, false, true>(plan, x, s, st)
-                  : launch_simtm_t<Env, EXENV_EULER, T, false, true>(plan, x, s, st);
-    return tsit ? launch_simtm_t<Env, EXENV_TSIT5, T, false, false>(plan, x, s, st)
-                : launch_simtm_t<Env, EXENV_EULER, T, false, false>(plan, x, s, st);
+      return tsit ? launch_simtm_w<Env, EXENV_TSIT5, T, true, true, 1>(plan, x, s, st)
+                  : launch_simtm_w<Env, EXENV_EULER, T, true, true, 1>(plan, x, s, st);
   }
+  if (generic)
+    return tsit ? launch_simtm_w<Env, EXENV_TSIT5, T, false, true, 1>(plan, x, s, st)
+                : launch_simtm_w<Env, EXENV_EULER, T, false, true, 1>(plan, x, s, st);
+  return tsit ? launch_simtm_fast<Env, EXENV_TSIT5, T>(plan, x, s, st) : launch_simtm_fast<Env, EXENV_EULER, T>(plan, x, s, st);
 }
 
 template <typename T>

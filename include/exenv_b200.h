@@ -168,7 +168,8 @@ typedef struct ExenvSimArgs {
   uint8_t *truncated;  /* optional (B, N+1, n_trunc) */
   uint8_t *terminated; /* optional (B, N) */
   int32_t tile_steps;  /* solver steps staged per shared-memory tile; 0 = auto */
-  int32_t block_envs;  /* reserved (the kernel uses 128 environments per CTA) */
+  int32_t block_envs;  /* batch-major: reserved (128 environments per CTA); time-major: environments per thread
+                          (1, 2 or 4; 0 = auto) */
   int32_t layout;      /* ExenvLayout of actions / obs / traj / reward / truncated / terminated */
   int32_t reserved_;
 } ExenvSimArgs;

@@ -107,3 +107,16 @@ if __name__ == "__main__":
         bench_sim("pmsm", ex.PMSM, ex.Euler(), f32, 1 << 18, 2500, **tm)
         bench_sim("pmsm_sat", ex.PMSM, ex.Tsit5(), f32, 1 << 17, 2500, saturated=True,
                   motor_variant=ex.MotorVariant.BRUSA, **tm)
+    if what in ("all", "simtm_v"):  # environments per thread of the time-major kernel
+        cases = [("msd", ex.MassSpringDamper, 1 << 20, 2000, {}), ("tank", ex.FluidTank, 1 << 20, 1000, {}),
+                 ("pendulum", ex.Pendulum, 1 << 20, 1000, {}), ("cartpole", ex.CartPole, 1 << 22, 200, {}),
+                 ("acrobot", ex.Acrobot, 1 << 22, 200, {}), ("pmsm", ex.PMSM, 1 << 18, 2500, {}),
+                 ("pmsm_sat", ex.PMSM, 1 << 17, 2500, dict(saturated=True, motor_variant=ex.MotorVariant.BRUSA))]
+        for name, cls, B, T, kw in cases:
+            for solver in (ex.Tsit5(), ex.Euler()):
+                for dt in (f32, f64):
+                    for v in (1, 2, 4):
+                        if v == 4 and name.startswith("pmsm"):
+                            continue
+                        bench_sim(name, cls, solver, dt, B if dt == f32 else B // 2, T, block_envs=v,
+                                  layout="time_major", iters=2, **kw)
