@@ -6,9 +6,12 @@ axis shards with no collective), diffrax-Tsit5 `vmap_sim_ahead` over 2000 steps 
 tau = 1e-4), float32, synthetic uniform(-1, 1) states/actions.  One bench "step" = one sim_ahead pass over the batch
 = B * 2000 env-steps, one launch of the persistent sm_100a kernel.
 
-  value      env-steps/s with inputs and outputs resident in HBM (device-timed with CUDA events, max over ranks)
-  e2e        the same call through the C ABI's host-buffer entry point (exenv_sim_ahead_host): pinned host inputs are
-             copied H2D, outputs D2H, inside the timed region
+  value      env-steps/s with inputs and outputs resident in HBM (device-timed with CUDA events, max over ranks), in the
+             layout named by --layout: `time_major` (default; the structure-of-arrays batch layout of the north star:
+             same logical arrays as the reference, batch axis innermost in memory) or `batch_major` (the reference's
+             C-contiguous arrays).  The other layout is timed in the same run and reported under "other_layout".
+  e2e        the same call through the C ABI's host-buffer entry point (exenv_sim_ahead_host): pinned host inputs in
+             the reference's layout are copied H2D, outputs D2H, inside the timed region
   roofline   algorithmic HBM bytes (S*(A+O+D) = 20 B per env-step) / measured launch time vs the measured copy peak
   cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, OpenMP over all host cores) --
              JAX/diffrax are not installable in this image, so the reference's own jit(vmap) cannot be timed.
@@ -39,6 +42,8 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--batch", type=int, default=B_PER_GPU, help="environments per GPU (default: the BASELINE config)")
+    p.add_argument("--layout", default="time_major", choices=["time_major", "batch_major"])
+    p.add_argument("--no-other-layout", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
@@ -48,6 +53,7 @@ def config_dict(args, batch):
     return {"workload": f"{ENV} batch={batch}/GPU Tsit5 vmap_sim_ahead {T_STEPS} steps tau={TAU} float32 "
                         f"(BASELINE.json configs[1])",
             "env": ENV, "solver": SOLVER, "batch_per_gpu": batch, "n_steps": T_STEPS, "tau": TAU,
+            "layout": getattr(args, "layout", None),
             "l2_policy": "inputs (8.4 GB actions) and outputs (33.6 GB) are far larger than the 126 MB L2",
             "parallelism": f"batch-sharded x{args.gpus}, no collective"}
 
@@ -152,16 +158,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch(batch):
-    """dram bytes of the dominant kernel from the committed `ncu --set full` summary, scaled to this launch."""
+KERNELS = {"time_major": ("simtm", "exenv::simtm_kernel<MassSpringDamper<float>, Tsit5, float, W=4, V=4>"),
+           "batch_major": ("sim", "exenv::sim_kernel<MassSpringDamper<float>, Tsit5, float>")}
+
+
+def ncu_facts(layout):
+    """Facts about the dominant kernel from the committed `ncu --set full` summaries (profiles/sim_kernel_traffic.json):
+    dram bytes per env-step (read + write), issue-slot and FMA-pipe utilisation."""
     p = ROOT / "profiles" / "sim_kernel_traffic.json"
-    if p.exists():
-        try:
-            d = json.load(open(p))
-            return d["dram_bytes_per_env_step"] * batch * T_STEPS
-        except Exception:
-            pass
-    return None
+    try:
+        return json.load(open(p))[layout]
+    except Exception:
+        return {}
 
 
 def run_b200(args):
@@ -184,12 +192,6 @@ def run_b200(args):
     env = ex.MassSpringDamper(batch_size=B, solver=ex.Tsit5(), tau=TAU, dtype=torch.float32, device=dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + 1000 * 2 + rank)
     _, state = env.vmap_reset(rng=gen)
-    actions = torch.rand((B, T_STEPS, A), device=dev, generator=gen) * 2 - 1
-    out = dict(obs=torch.empty((B, T_STEPS + 1, O), device=dev),
-               traj=[torch.empty((B, T_STEPS + 1), device=dev) for _ in range(D)])
-
-    def step():
-        return env._sim_impl(env.env_properties, B, state, actions, TAU, TAU, out=out)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -197,25 +199,61 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = ex.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    launches = ex.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    elapsed = e0.elapsed_time(e1) * 1e-3
-    t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_max = float(t.item())
+    def buffers(layout):
+        """Synthetic actions and preallocated outputs in the physical layout of `layout`."""
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        if layout == "time_major":
+            acts = (torch.rand((T_STEPS, B, A), device=dev, generator=g) * 2 - 1).permute(1, 0, 2)  # logical (B, T, A)
+            out = dict(obs=torch.empty((T_STEPS + 1, B, O), device=dev),
+                       traj=[torch.empty((T_STEPS + 1, B), device=dev) for _ in range(D)])
+        else:
+            acts = torch.rand((B, T_STEPS, A), device=dev, generator=g) * 2 - 1
+            out = dict(obs=torch.empty((B, T_STEPS + 1, O), device=dev),
+                       traj=[torch.empty((B, T_STEPS + 1), device=dev) for _ in range(D)])
+        return acts, out
+
+    def timed(layout, n_steps, n_warm, sample_clocks):
+        acts, out = buffers(layout)
+
+        def step():
+            return env._sim_impl(env.env_properties, B, state, acts, TAU, TAU, out=out, layout=layout)
+
+        for _ in range(n_warm):
+            step()
+        barrier()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        launches0 = ex.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            step()
+        e1.record()
+        barrier()
+        launches = ex.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        elapsed = e0.elapsed_time(e1) * 1e-3
+        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(elapsed=elapsed, elapsed_max=float(t.item()), launches=launches, clocks=clocks, acts=acts, out=out)
+
+    main = timed(args.layout, args.steps, args.warmup, True)
+    elapsed, elapsed_max, launches, clocks = main["elapsed"], main["elapsed_max"], main["launches"], main["clocks"]
     value = world * B * T_STEPS * args.steps / elapsed_max
+    other = None
+    if not args.no_other_layout:
+        main.pop("acts"), main.pop("out")  # free 42 GB before the second set of buffers
+        torch.cuda.empty_cache()
+        o_layout = "batch_major" if args.layout == "time_major" else "time_major"
+        n_o = max(1, min(args.steps, 5))
+        r = timed(o_layout, n_o, 3, False)
+        other = {"layout": o_layout, "value": world * B * T_STEPS * n_o / r["elapsed_max"], "unit": "env-steps/s",
+                 "ms_per_step": r["elapsed_max"] / n_o * 1e3, "steps": n_o,
+                 "roofline_frac": BYTES_PER_ENV_STEP * B * T_STEPS / (r["elapsed"] / n_o) / 1e9 / measured_peak_gbs()[0],
+                 "kernel": KERNELS[o_layout][1]}
+        del r
+    main.pop("acts", None), main.pop("out", None)
+    torch.cuda.empty_cache()
 
     # ---- end to end through the C ABI with host buffers (rank-local, then max over ranks)
     e2e = None
@@ -224,7 +262,8 @@ def run_b200(args):
         NS = T_STEPS + 1
         try:
             h_state = [getattr(state.physical_state, n).cpu().pin_memory() for n in env.PHYS_FIELDS]
-            h_act = actions.cpu().pin_memory()
+            g = torch.Generator().manual_seed(7 + rank)
+            h_act = (torch.rand((B, T_STEPS, A), generator=g) * 2 - 1).pin_memory()
             h_obs = torch.empty((B, NS, O), dtype=torch.float32).pin_memory()
             h_traj = [torch.empty((B, NS), dtype=torch.float32).pin_memory() for _ in range(D)]
             h_last = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(D)]
@@ -246,7 +285,12 @@ def run_b200(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             h2d = h_act.numel() * 4 + sum(x.numel() for x in h_state) * 4
             d2h = h_obs.numel() * 4 + sum(x.numel() for x in h_traj) * 4 + sum(x.numel() for x in h_last) * 4
-            ok = bool(torch.equal(h_obs[:64], out["obs"][:64].cpu()))
+            # check a slice of the host-buffer result against a device-resident call on the same 64 environments
+            env64 = ex.MassSpringDamper(batch_size=64, solver=ex.Tsit5(), tau=TAU, dtype=torch.float32, device=dev)
+            _, st64 = env64.vmap_reset()
+            st64.physical_state = env64.PhysicalState(*[x[:64].to(dev) for x in h_state])
+            chk = env64.vmap_sim_ahead(st64, h_act[:64].to(dev), TAU, TAU)[0].cpu()
+            ok = bool(torch.equal(h_obs[:64], chk))
             e2e = {"value": world * B * T_STEPS * n_e2e / float(tt.item()), "unit": "env-steps/s",
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
                    "matches_device_path": ok,
@@ -259,6 +303,7 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        facts = ncu_facts(args.layout)
         launch_s = elapsed / args.steps  # one launch per step on this rank
         achieved = BYTES_PER_ENV_STEP * B * T_STEPS / launch_s / 1e9
         line = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
@@ -267,9 +312,15 @@ def run_b200(args):
                 "data": "synthetic", "config": config_dict(args, B), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": ncu_traffic_per_launch(B), "peak_source": peak_src,
-                             "kernel": "exenv::sim_kernel<MassSpringDamper<float>, Tsit5, float>",
-                             "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP}}
+                             "frac": achieved / peak,
+                             "traffic": (facts["dram_bytes_per_env_step"] * B * T_STEPS) if facts else None,
+                             "peak_source": peak_src, "kernel": KERNELS[args.layout][1],
+                             "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
+                             "ncu": {k: facts.get(k) for k in ("issue_slots_busy", "fma_pipe_busy", "dram_pct_of_peak",
+                                                                "warp_instructions_per_env_step", "source")},
+                             "note": "the Tsit5 trajectory kernel is bound by instruction issue (7 right-hand sides + "
+                                     "dense output per env-step), not by HBM; see profiles/README.md"},
+                "other_layout": other}
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline()

@@ -662,15 +662,20 @@ static int launch_simtm_w(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
 // saturated PMSM) are bound by their own arithmetic and registers.
 template <class Env, int SOLVER, typename T>
 constexpr int simtm_auto_v() {
-  if (Env::ID == 4) return SOLVER == EXENV_TSIT5 ? 1 : 2;
-  if (Env::IS_PMSM) return Env::SATURATED ? 1 : 2;
-  if (Env::ID == 3) return 2;
-  return sizeof(T) == 4 ? 4 : 2;
+  constexpr bool f32 = sizeof(T) == 4, tsit = SOLVER == EXENV_TSIT5;
+  if (Env::IS_PMSM) return 1;
+  switch (Env::ID) {
+    case 0: return tsit ? (f32 ? 2 : 1) : (f32 ? 4 : 1);  // pendulum
+    case 1: return tsit ? (f32 ? 4 : 2) : (f32 ? 2 : 1);  // mass-spring-damper
+    case 2: return tsit ? (f32 ? 4 : 1) : (f32 ? 4 : 2);  // fluid tank
+    case 3: return tsit ? 1 : 2;                          // cart-pole
+    default: return tsit ? 1 : (f32 ? 2 : 1);             // acrobot
+  }
 }
 
 template <class Env, int SOLVER, typename T>
 static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
-  constexpr int VMAX = Env::IS_PMSM ? 2 : 4;  // instantiated widths: 1, 2, (4)
+  constexpr int VMAX = Env::IS_PMSM ? 1 : 4;  // instantiated widths: 1, (2, 4)
   int v = x.block_envs > 0 ? x.block_envs : simtm_auto_v<Env, SOLVER, T>();
   if (v > VMAX) v = VMAX;
   if (v == 3) v = 2;
@@ -692,7 +697,9 @@ static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const
   if constexpr (VMAX >= 4) {
     if (v == 4) return launch_simtm_w<Env, SOLVER, T, false, false, 4>(plan, x, sch, stream);
   }
-  if (v == 2) return launch_simtm_w<Env, SOLVER, T, false, false, 2>(plan, x, sch, stream);
+  if constexpr (VMAX >= 2) {
+    if (v == 2) return launch_simtm_w<Env, SOLVER, T, false, false, 2>(plan, x, sch, stream);
+  }
   return launch_simtm_w<Env, SOLVER, T, false, false, 1>(plan, x, sch, stream);
 }
 
