@@ -69,8 +69,10 @@ struct ExenvPlan {
 namespace exenv {
 
 // per-dtype translation units (exenv_step_f32.cu, exenv_step_f64.cu, exenv_sim_f32.cu, exenv_sim_f64.cu)
-int launch_step_f32(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
-int launch_step_f64(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
+int launch_step_euler_f32(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
+int launch_step_euler_f64(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
+int launch_step_tsit5_f32(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
+int launch_step_tsit5_f64(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream);
 int launch_reset_f32(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream);
 int launch_reset_f64(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream);
 int launch_epilogue_f32(const ExenvPlan &plan, const ExenvEpilogueArgs &a, cudaStream_t stream);
@@ -83,7 +85,9 @@ size_t sim_smem_bytes_f32(const ExenvPlan &plan, int step_cap, int act_cap, int 
 size_t sim_smem_bytes_f64(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);
 
 inline int launch_step(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t s) {
-  return plan.desc.dtype == EXENV_F64 ? launch_step_f64(plan, a, s) : launch_step_f32(plan, a, s);
+  if (plan.desc.solver == EXENV_TSIT5)
+    return plan.desc.dtype == EXENV_F64 ? launch_step_tsit5_f64(plan, a, s) : launch_step_tsit5_f32(plan, a, s);
+  return plan.desc.dtype == EXENV_F64 ? launch_step_euler_f64(plan, a, s) : launch_step_euler_f32(plan, a, s);
 }
 inline int launch_reset(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t s) {
   return plan.desc.dtype == EXENV_F64 ? launch_reset_f64(plan, a, s) : launch_reset_f32(plan, a, s);

@@ -125,9 +125,12 @@ EX_HD void env_step_one(T *s, const T *a, const T *p, typename Env::Aux &aux, T 
 #pragma unroll
     for (int i = 0; i < NODE; ++i) y0[i] = s[i];
   }
+  // Tsit5 (instruction bound): divisions by parameter-only denominators through the prepared reciprocal (correctly
+  // rounded, exenv_math.cuh); Euler (HBM bound, golden-vector replay): the plain IEEE operator
+  constexpr bool FD = SOLVER == EXENV_TSIT5;
   T f0[NODE];
   const typename Env::Pre pre = Env::precompute(p);
-  Env::template rhs<false>(y0, u, p, pre, aux, f0);
+  Env::template rhs<FD>(y0, u, p, pre, aux, f0);
   if constexpr (SOLVER == EXENV_EULER) {  // diffrax.Euler: y1 = y0 + (t1 - t0) * f(t0, y0)
 #pragma unroll
     for (int i = 0; i < NODE; ++i) {
@@ -137,7 +140,7 @@ EX_HD void env_step_one(T *s, const T *a, const T *p, typename Env::Aux &aux, T 
   } else {
     T k[7][NODE];
     tsit5_step<T, NODE>(
-        y0, f0, tau, [&](int, const T *ys, T *f) { Env::template rhs<false>(ys, u, p, pre, aux, f); }, y1, f_last, k);
+        y0, f0, tau, [&](int, const T *ys, T *f) { Env::template rhs<FD>(ys, u, p, pre, aux, f); }, y1, f_last, k);
   }
   Env::post(y1);
   if constexpr (Env::IS_PMSM) {

@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetK<T> a, const KPa
 }
 
 // reward / truncated / terminated of given states: one thread per state.
+#if EXENV_STEP_SOLVER == 0
 template <typename T>
 struct EpiK {
   long B;
@@ -371,6 +372,8 @@ int EXENV_CAT(launch_epilogue_, EXENV_SFX)(const ExenvPlan &plan, const ExenvEpi
   return EXENV_ERR_INVALID;
 }
 
+#endif  // epilogue: Euler translation unit only
+
 // ---- launchers ---------------------------------------------------------------------------------------------------
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -435,6 +438,7 @@ static int launch_step_t(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStre
   return EXENV_OK;
 }
 
+#if EXENV_STEP_SOLVER == 0
 template <class Env, typename T, bool PER_ENV>
 static int launch_reset_t(const ExenvPlan &plan, const ExenvResetArgs &x, cudaStream_t stream) {
   ResetK<T> a{};
@@ -460,20 +464,31 @@ static int launch_reset_t(const ExenvPlan &plan, const ExenvResetArgs &x, cudaSt
   return EXENV_OK;
 }
 
+#endif
+
+// One translation unit per solver (EXENV_STEP_SOLVER): the Euler instantiations are compiled with -fmad=false (HBM
+// bound; golden-vector replay), the Tsit5 ones with FMA contraction (7 right-hand sides per step: instruction bound).
 template <class Env, typename T>
 static int step_dispatch2(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStream_t st) {
-  const bool tsit = plan.desc.solver == EXENV_TSIT5;
   if constexpr (Env::IS_PMSM) {  // PMSM properties are static jit arguments in the reference: shared only
-    return tsit ? launch_step_t<Env, EXENV_TSIT5, T, false>(plan, x, st)
-                : launch_step_t<Env, EXENV_EULER, T, false>(plan, x, st);
+    return launch_step_t<Env, EXENV_STEP_SOLVER, T, false>(plan, x, st);
   } else {
-    if (plan.per_env)
-      return tsit ? launch_step_t<Env, EXENV_TSIT5, T, true>(plan, x, st)
-                  : launch_step_t<Env, EXENV_EULER, T, true>(plan, x, st);
-    return tsit ? launch_step_t<Env, EXENV_TSIT5, T, false>(plan, x, st)
-                : launch_step_t<Env, EXENV_EULER, T, false>(plan, x, st);
+    if (plan.per_env) return launch_step_t<Env, EXENV_STEP_SOLVER, T, true>(plan, x, st);
+    return launch_step_t<Env, EXENV_STEP_SOLVER, T, false>(plan, x, st);
   }
 }
+
+// PMSM is ill-conditioned enough (cancellation in the voltage equations, 2x2 LU of the flux-map Jacobian) for FMA
+// contraction to move a single Tsit5 step by more than the per-step parity tolerance, so its Tsit5 instantiations
+// live in the un-contracted translation unit as well.
+int EXENV_CAT(launch_step_tsit5_pmsm_, EXENV_SFX)(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStream_t st);
+#if EXENV_STEP_SOLVER == 0
+int EXENV_CAT(launch_step_tsit5_pmsm_, EXENV_SFX)(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStream_t st) {
+  using T = EXENV_REAL;
+  if (plan.desc.flags & EXENV_FLAG_SATURATED) return launch_step_t<Pmsm<T, true>, EXENV_TSIT5, T, false>(plan, x, st);
+  return launch_step_t<Pmsm<T, false>, EXENV_TSIT5, T, false>(plan, x, st);
+}
+#endif
 
 template <typename T>
 static int step_dispatch(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStream_t st) {
@@ -484,14 +499,23 @@ static int step_dispatch(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStre
     case EXENV_CART_POLE: return step_dispatch2<CartPole<T>, T>(plan, x, st);
     case EXENV_ACROBOT: return step_dispatch2<Acrobot<T>, T>(plan, x, st);
     case EXENV_PMSM:
+#if EXENV_STEP_SOLVER == 1
+      return EXENV_CAT(launch_step_tsit5_pmsm_, EXENV_SFX)(plan, x, st);
+#else
       if (plan.desc.flags & EXENV_FLAG_SATURATED) return step_dispatch2<Pmsm<T, true>, T>(plan, x, st);
       return step_dispatch2<Pmsm<T, false>, T>(plan, x, st);
+#endif
   }
   set_error("unknown env %d", plan.desc.env);
   return EXENV_ERR_INVALID;
 }
 
-int EXENV_CAT(launch_step_, EXENV_SFX)(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream) {
+#if EXENV_STEP_SOLVER == 1
+int EXENV_CAT(launch_step_tsit5_, EXENV_SFX)(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream) {
+  return step_dispatch<EXENV_REAL>(plan, a, stream);
+}
+#else
+int EXENV_CAT(launch_step_euler_, EXENV_SFX)(const ExenvPlan &plan, const ExenvStepArgs &a, cudaStream_t stream) {
   return step_dispatch<EXENV_REAL>(plan, a, stream);
 }
 
@@ -520,5 +544,7 @@ static int reset_dispatch(const ExenvPlan &plan, const ExenvResetArgs &x, cudaSt
 int EXENV_CAT(launch_reset_, EXENV_SFX)(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream) {
   return reset_dispatch<EXENV_REAL>(plan, a, stream);
 }
+
+#endif  // Euler translation unit: reset + epilogue
 
 }  // namespace exenv
