@@ -124,3 +124,60 @@ def test_error_paths(excenvs):
         excenvs.PMSM(batch_size=2, saturated=True)  # DEFAULT motor has no LUT (pmsm_env.py:189-193)
     with pytest.raises(ValueError):
         excenvs.Pendulum(batch_size=2, static_params={"g": [9.81, 9.81], "l": 2, "m": 1})  # list rejected
+
+
+def test_readme_example_config1(excenvs):
+    """BASELINE.json configs[0] = the reference's README example (README.md:15-33): PENDULUM batch_size=5, explicit
+    Euler, tau=2e-2, torque normalisation +-15, 1000 sequential vmap_step calls with actions linspace(-1, 1, 1000)
+    repeated over the batch, default reset -- replayed by the oracle; the five trajectories are identical."""
+    B, N = 5, 1000
+    env = excenvs.EnvironmentRegistry.PENDULUM.make(
+        batch_size=B, action_normalizations={"torque": excenvs.MinMaxNormalization(min=-15, max=15)}, tau=2e-2)
+    orc = O.Oracle("pendulum", solver=O.EULER, dtype=np.float32, tau=2e-2, action_normalizations={"torque": (-15.0, 15.0)})
+    obs, state = env.vmap_reset()
+    actions = torch.linspace(-1, 1, N, device="cuda")[None, :, None].repeat(B, 1, 1)
+    observations = [obs]
+    for idx in range(N):
+        obs, state = env.vmap_step(state, actions[:, idx, :])
+        observations.append(obs)
+    observations = torch.stack(observations, dim=1)
+    assert observations.shape == (B, N + 1, 2)
+    assert all(torch.equal(observations[0], observations[b]) for b in range(1, B))
+    st = [np.full(B, np.pi, np.float32), np.zeros(B, np.float32)]  # default reset: theta = pi, omega = 0
+    acts = np_(actions)
+    cur = st
+    out = []
+    for idx in range(N):
+        r = orc.step(cur, acts[:, idx, :])
+        cur = r["state"]
+        out.append(r["obs"])
+    out = np.stack(out, axis=1)
+    got = np_(observations)[:, 1:]
+    # 1000 closed-loop fp32 Euler steps of a pendulum swinging through several revolutions: libm-level differences
+    # (sinf) accumulate; the per-step bound (1e-6) is asserted by test_step_matches_oracle
+    assert np.max(np.abs(got - out)) < 5e-3
+    assert np.max(np.abs(got[:, :50] - out[:, :50])) < 1e-5
+
+
+def test_step_is_cuda_graph_capturable(excenvs):
+    """include/exenv_b200.h: launches are asynchronous on the caller's stream, no host synchronisation, no allocation
+    -> a vmap_step call can be captured into a CUDA graph and replayed (launch-latency regime of configs[0])."""
+    B = 5
+    env = excenvs.Pendulum(batch_size=B, tau=2e-2, dtype=torch.float32)
+    _, s_eager = env.vmap_reset()
+    _, s_graph = env.vmap_reset()
+    action = torch.zeros((B, 1), device="cuda")
+    env.vmap_step(s_graph, action)  # plan creation happens outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            obs_g, s_out = env.vmap_step(s_graph, action, inplace=True)
+    for i in range(20):
+        action.fill_(0.1 * (i % 5) - 0.2)
+        obs_e, s_eager = env.vmap_step(s_eager, action)
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(obs_e, obs_g)
+    assert torch.equal(s_eager.physical_state.theta, s_out.physical_state.theta)

@@ -120,3 +120,48 @@ if __name__ == "__main__":
                             continue
                         bench_sim(name, cls, solver, dt, B if dt == f32 else B // 2, T, block_envs=v,
                                   layout="time_major", iters=2, **kw)
+    if what in ("all", "config1"):  # BASELINE configs[0]: the launch-latency regime (pendulum, B = 5, Euler, tau = 2e-2)
+        B, N = 5, 1000
+        env = ex.EnvironmentRegistry.PENDULUM.make(batch_size=B, tau=2e-2,
+                                                   action_normalizations={"torque": ex.MinMaxNormalization(min=-15, max=15)})
+        _, state = env.vmap_reset()
+        actions = torch.linspace(-1, 1, N, device="cuda")[None, :, None].repeat(B, 1, 1)
+        for i in range(50):
+            _, state = env.vmap_step(state, actions[:, i, :])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(N):
+            _, state = env.vmap_step(state, actions[:, i, :])
+        torch.cuda.synchronize()
+        t_eager = (time.perf_counter() - t0) / N
+        # the same 1000 launches captured once into a CUDA graph (in-place state, actions read from the (B, T, A) tensor)
+        _, sg = env.vmap_reset()
+        acts = [actions[:, i, :].contiguous() for i in range(N)]
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                s = sg
+                for i in range(N):
+                    _, s = env.vmap_step(s, acts[i], inplace=True)
+        g.replay()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            g.replay()
+        torch.cuda.synchronize()
+        t_graph = (time.perf_counter() - t0) / (10 * N)
+        # one persistent sim_ahead launch over the same 1000 actions
+        env2 = ex.EnvironmentRegistry.PENDULUM.make(batch_size=B, tau=2e-2,
+                                                    action_normalizations={"torque": ex.MinMaxNormalization(min=-15, max=15)})
+        _, s2 = env2.vmap_reset()
+        env2.vmap_sim_ahead(s2, actions, 2e-2, 2e-2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            env2.vmap_sim_ahead(s2, actions, 2e-2, 2e-2)
+        torch.cuda.synchronize()
+        t_sim = (time.perf_counter() - t0) / (10 * N)
+        print(json.dumps(dict(kind="config1", B=B, N=N, us_per_step_eager=t_eager * 1e6, us_per_step_graph=t_graph * 1e6,
+                              us_per_step_sim_ahead=t_sim * 1e6, env_steps_per_s_eager=B / t_eager,
+                              env_steps_per_s_graph=B / t_graph, env_steps_per_s_sim_ahead=B / t_sim)), flush=True)
