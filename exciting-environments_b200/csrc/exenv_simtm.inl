@@ -69,10 +69,16 @@ __device__ __forceinline__ void stcs_chunk(void *dst, const void *src) {
     float2 t;
     memcpy(&t, src, 8);
     __stcs(reinterpret_cast<float2 *>(dst), t);
-  } else {
+  } else if constexpr (BYTES == 4) {
     float t;
     memcpy(&t, src, 4);
     __stcs(reinterpret_cast<float *>(dst), t);
+  } else if constexpr (BYTES == 2) {
+    unsigned short t;
+    memcpy(&t, src, 2);
+    __stcs(reinterpret_cast<unsigned short *>(dst), t);
+  } else {
+    __stcs(reinterpret_cast<unsigned char *>(dst), *reinterpret_cast<const unsigned char *>(src));
   }
 }
 // Loads are volatile asm: the kernel orders them by hand (see the solver loop) and ptxas must neither merge them into
@@ -232,15 +238,19 @@ __device__ __forceinline__ void staged_to_fields(const T *st, T omega_el, T *sv)
 // V consecutive environments per thread: their leaves / action rows / observation rows are moved with one vector
 // access each, and the per-step bookkeeping (schedule fetch and decode, window slide, pointer updates, loop) is paid
 // once for V env-steps.  V > 1 needs B % V == 0 and V * sizeof(T)-aligned buffers (the launcher checks).
+// EPI: the fast instantiation with vmap_generate_rew_trunc_term_ahead (core_env.py:618-647) fused for
+// control_state == [] (reward is the constant 0 there): truncated for every saved state, reward / terminated for
+// states[1:], written as V-wide vectors like the leaves.
 // GENERIC (V == 1 only): reference entries in the observation (control_state != []), the fused reward / truncated /
 // terminated outputs (vmap_generate_rew_trunc_term_ahead, core_env.py:618-647), per-environment parameters, skipped
 // (NULL) trajectory leaves.
-template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V>
+template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
 __global__ void __launch_bounds__(SIMTM_THREADS)
     simtm_kernel(const __grid_constant__ SimTmK<T> a, const __grid_constant__ KParams<T> kp) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
   constexpr int NST = staged_values<Env>();
   static_assert(!GENERIC || V == 1, "the generic instantiation handles one environment per thread");
+  static_assert(!(GENERIC && EPI), "EPI is the fused-epilogue flavour of the fast instantiation");
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
   const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;  // first environment of this thread
@@ -408,6 +418,20 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
 #pragma unroll
   for (int d = 0; d < D; ++d) tp[d] = a.traj[d] ? a.traj[d] + b : nullptr;
   T *op = a.obs + b * OW;
+  constexpr int NT0 = trunc_dim<Env>(0);  // truncated width without reference entries
+  T *rwp = EPI ? a.reward + b : nullptr;  // rows of states[1:]: they start moving after save 0
+  uint8_t *trp = EPI ? a.trunc + b * NT0 : nullptr;
+  uint8_t *tmp = EPI ? a.term + b : nullptr;
+  auto flags_fast = [&](const T *sv, const T *ob, uint8_t *tr, uint8_t &te) {  // control_state == []
+    bool t0 = false;
+#pragma unroll
+    for (int i = 0; i < NT0; ++i) {
+      const bool tv = trunc_entry<Env, T>(i, sv, ob, p);
+      if (i == 0) t0 = tv;
+      tr[i] = tv;
+    }
+    te = terminated_of<Env, T>((T)0, t0);
+  };
   T stash[V][NST];
   long step_first_save = 0;  // save index the running pointers address
   auto obs_fast = [&](int v, const T *st, const T *sv, T *ob) {
@@ -441,6 +465,16 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
         obs_fast(v, st, sv, ob);
 #pragma unroll
         for (int o = 0; o < O; ++o) __stcs(op + roff * O + o, ob[o]);
+        if constexpr (EPI) {
+          uint8_t tr[NT0], te;
+          flags_fast(sv, ob, tr, te);
+#pragma unroll
+          for (int i = 0; i < NT0; ++i) trp[roff * NT0 + i] = tr[i];
+          // reward / terminated rows run one save behind (states[1:]); sidx > step_first_save >= 0 here
+          const size_t r1 = (size_t)(sidx - step_first_save - (step_first_save == 0 ? 1 : 0)) * Bu + v;
+          __stcs(rwp + r1, (T)0);
+          tmp[r1] = te;
+        }
       }
     } else {
       const size_t row = (size_t)sidx * Bu + b;
@@ -494,6 +528,24 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
       }
       store_vec<T, V * O>(op, &ob[0][0]);
       op += (size_t)Bu * (unsigned)(ns * O);
+      if constexpr (EPI) {
+        uint8_t tr[V][NT0], te[V];
+        T zero[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          flags_fast(sv[v], ob[v], tr[v], te[v]);
+          zero[v] = (T)0;
+        }
+        store_vec<uint8_t, V * NT0>(trp, &tr[0][0]);
+        trp += (size_t)Bu * (unsigned)(ns * NT0);
+        if (step_first_save > 0) {  // save 0 has no reward / terminated entry
+          store_vec<T, V>(rwp, zero);
+          store_vec<uint8_t, V>(tmp, te);
+        }
+        const unsigned adv = (unsigned)(step_first_save > 0 ? ns : ns - 1);
+        rwp += (size_t)Bu * adv;
+        tmp += (size_t)Bu * adv;
+      }
     }
   };
 
@@ -590,7 +642,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------------------
-template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V>
+template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
 static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
   SimTmK<T> a{};
   a.B = x.batch;
@@ -627,7 +679,7 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   KParams<T> kp = make_kparams<T>(plan);
   size_t smem = 0;
   if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = plan.lut.bytes + 16;
-  auto kern = simtm_kernel<Env, SOLVER, T, PER_ENV, GENERIC, W, V>;
+  auto kern = simtm_kernel<Env, SOLVER, T, PER_ENV, GENERIC, W, V, EPI>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -649,10 +701,10 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
 
 // Window length: 2 covers every schedule whose steps read at most two consecutive ZOH indices (always the case up to
 // floating-point lag of the accumulated solver time); 4 is the general case (build_schedule_t rejects more).
-template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int V>
+template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int V, bool EPI = false>
 static int launch_simtm_w(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
-  if (sch.win_need <= 2) return launch_simtm_v<Env, SOLVER, T, PER_ENV, GENERIC, 2, V>(plan, x, sch, stream);
-  if (sch.win_need <= 4) return launch_simtm_v<Env, SOLVER, T, PER_ENV, GENERIC, 4, V>(plan, x, sch, stream);
+  if (sch.win_need <= 2) return launch_simtm_v<Env, SOLVER, T, PER_ENV, GENERIC, 2, V, EPI>(plan, x, sch, stream);
+  if (sch.win_need <= 4) return launch_simtm_v<Env, SOLVER, T, PER_ENV, GENERIC, 4, V, EPI>(plan, x, sch, stream);
   set_error("sim_ahead (time-major): a solver step needs %d consecutive actions (> 4)", sch.win_need);
   return EXENV_ERR_UNSUPPORTED;
 }
@@ -691,9 +743,18 @@ static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const
     bool r = al(x.actions, arow) && al(x.obs, orow);
     for (int d = 0; d < Env::D; ++d) r = r && al(x.state_in[d], leaf) && al(x.traj[d], leaf) && al(x.last[d], leaf);
     for (int d = 0; d < Env::NODE; ++d) r = r && al(x.k_last[d], leaf);
+    if (x.reward) {
+      const size_t trow = std::min<size_t>(16, (size_t)vv * trunc_dim<Env>(0));
+      r = r && al(x.reward, leaf) && al(x.truncated, trow) && al(x.terminated, (size_t)vv);
+    }
     return r;
   };
   while (v > 1 && !ok(v)) v >>= 1;
+  if (x.reward) {  // fused epilogue (control_state == []): the tuned width or one environment per thread
+    constexpr int VA = simtm_auto_v<Env, SOLVER, T>() > VMAX ? VMAX : simtm_auto_v<Env, SOLVER, T>();
+    if (v == VA) return launch_simtm_w<Env, SOLVER, T, false, false, VA, true>(plan, x, sch, stream);
+    return launch_simtm_w<Env, SOLVER, T, false, false, 1, true>(plan, x, sch, stream);
+  }
   if constexpr (VMAX >= 4) {
     if (v == 4) return launch_simtm_w<Env, SOLVER, T, false, false, 4>(plan, x, sch, stream);
   }
@@ -706,9 +767,11 @@ static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const
 template <class Env, typename T>
 static int simtm_dispatch2(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &s, cudaStream_t st) {
   const bool tsit = plan.desc.solver == EXENV_TSIT5;
-  // anything beyond the plain call takes the GENERIC instantiation: reference entries, the fused epilogue, skipped
-  // (NULL) trajectory leaves, observation rows that cannot be written with aligned vector stores
-  bool generic = plan.desc.n_control > 0 || x.reward || x.truncated || x.terminated;
+  // anything beyond the plain call (optionally with all three epilogue outputs) takes the GENERIC instantiation:
+  // reference entries, a partial epilogue, skipped (NULL) trajectory leaves, observation rows that cannot be written
+  // with aligned vector stores
+  const bool epi_any = x.reward || x.truncated || x.terminated, epi_all = x.reward && x.truncated && x.terminated;
+  bool generic = plan.desc.n_control > 0 || (epi_any && !epi_all);
   for (int d = 0; d < Env::D; ++d) generic |= x.traj[d] == nullptr;
   {
     const size_t row_bytes = (size_t)Env::O * sizeof(T);

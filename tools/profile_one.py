@@ -15,6 +15,7 @@ T = int(sys.argv[6]) if len(sys.argv) > 6 else 500
 tile = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 blk = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 tm = len(sys.argv) > 9 and sys.argv[9] == "tm"
+epi = len(sys.argv) > 10 and sys.argv[10] == "epi"  # fused reward / truncated / terminated outputs
 dtype = torch.float32 if dt == "f32" else torch.float64
 kw = dict(saturated=True, motor_variant=ex.MotorVariant.BRUSA) if name == "pmsm_sat" else {}
 env = ENVS[name](batch_size=B, solver=ex.Tsit5() if solver == "tsit5" else ex.Euler(), dtype=dtype, **kw)
@@ -31,7 +32,8 @@ if kind == "sim":
         out = dict(obs=torch.empty((B, T + 1, env.obs_dim), device="cuda", dtype=dtype),
                    traj=[torch.empty((B, T + 1), device="cuda", dtype=dtype) for _ in range(env.physical_state_dim)])
     fn = lambda: env._sim_impl(env.env_properties, B, state, actions, env.tau, env.tau, tile_steps=tile,
-                               block_envs=blk, out=out, layout="time_major" if tm else "batch_major")
+                               block_envs=blk, out=out, layout="time_major" if tm else "batch_major",
+                               epilogue=epi)
     units = B * T
 else:
     action = torch.rand((B, env.action_dim), device="cuda", dtype=dtype) * 2 - 1
@@ -46,4 +48,4 @@ for _ in range(3):
 e1.record()
 torch.cuda.synchronize()
 t = e0.elapsed_time(e1) / 3 * 1e-3
-print(f"{kind} {name} {solver} {dt} {'tm' if tm else 'bm'} B={B} T={T} tile={tile} blk={blk}: {t*1e3:.3f} ms  {units/t:.4e} env-steps/s")
+print(f"{kind} {name} {solver} {dt} {'tm' if tm else 'bm'}{' epi' if kind == 'sim' and epi else ''} B={B} T={T} tile={tile} blk={blk}: {t*1e3:.3f} ms  {units/t:.4e} env-steps/s")
