@@ -413,7 +413,9 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
     L.ny = ny;
     L.off_gy = pad16((size_t)nx * es);
     L.off_cells = L.off_gy + pad16((size_t)ny * es);
-    L.bytes = L.off_cells + pad16((size_t)nx * ny * 6 * es);
+    L.off_wx = L.off_cells + pad16((size_t)nx * ny * 6 * es);
+    L.off_wy = L.off_wx + pad16((size_t)(nx - 1) * 2 * es);
+    L.bytes = L.off_wy + pad16((size_t)(ny - 1) * 2 * es);
     L.inv_dx = 1.0 / (desc->lut_gx[1] - desc->lut_gx[0]);
     L.inv_dy = 1.0 / (desc->lut_gy[1] - desc->lut_gy[0]);
     std::vector<unsigned char> blob(L.bytes, 0);
@@ -425,6 +427,27 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
     };
     for (int i = 0; i < nx; ++i) put(0, (size_t)i, desc->lut_gx[i]);
     for (int j = 0; j < ny; ++j) put(L.off_gy, (size_t)j, desc->lut_gy[j]);
+    // per-cell {width, reciprocal} in the plan dtype, computed like the kernel would: d = RN(g[i+1] - g[i]) on the
+    // dtype-rounded grid values, r = RN(1 / d)
+    auto widths = [&](const double *g, int n, size_t off) {
+      bool regular = true;
+      const double d0 = (g[n - 1] - g[0]) / (n - 1);
+      for (int i = 0; i + 1 < n; ++i) {
+        if (es == 8) {
+          const double d = g[i + 1] - g[i];
+          put(off, (size_t)2 * i, d);
+          put(off, (size_t)2 * i + 1, 1.0 / d);
+        } else {
+          const float d = (float)g[i + 1] - (float)g[i];
+          put(off, (size_t)2 * i, d);
+          put(off, (size_t)2 * i + 1, 1.0f / d);
+        }
+        regular = regular && std::fabs(g[i] - (g[0] + i * d0)) < 0.25 * std::fabs(d0);
+      }
+      return regular && d0 > 0;
+    };
+    const bool rx = widths(desc->lut_gx, nx, L.off_wx), ry = widths(desc->lut_gy, ny, L.off_wy);
+    L.regular = rx && ry;
     for (int q = 0; q < 6; ++q)
       for (int i = 0; i < nx; ++i)
         for (int j = 0; j < ny; ++j)

@@ -22,13 +22,48 @@ struct LutView {
   const T *cells;
   int nx, ny;
   T inv_dx, inv_dy;  // 1 / grid spacing: only used for the initial cell guess
+  // optional (NULL: plain IEEE division): per grid cell {width d = g[i+1] - g[i], RN(1 / d)} for the correctly rounded
+  // reciprocal division of exenv_math.cuh
+  const T *wx;
+  const T *wy;
+  int regular;  // both grids are equidistant up to rounding: the initial guess is at most one cell off
 };
+
+// Where the sections of the device blob prepared at plan creation live (exenv_api.cu), for building a LutView over
+// the global copy (step kernel) or a shared-memory copy (sim_ahead kernels).
+template <typename T>
+struct LutGeom {
+  unsigned bytes, off_gy, off_cells, off_wx, off_wy;
+  int nx, ny, regular;
+  T inv_dx, inv_dy;
+};
+template <typename T>
+EX_HD LutView<T> lut_view_at(const void *base, const LutGeom<T> &g) {
+  const char *b = (const char *)base;
+  LutView<T> L;
+  L.gx = (const T *)b;
+  L.gy = (const T *)(b + g.off_gy);
+  L.cells = (const T *)(b + g.off_cells);
+  L.wx = (const T *)(b + g.off_wx);
+  L.wy = (const T *)(b + g.off_wy);
+  L.nx = g.nx;
+  L.ny = g.ny;
+  L.regular = g.regular;
+  L.inv_dx = g.inv_dx;
+  L.inv_dy = g.inv_dy;
+  return L;
+}
 
 // searchsorted(g, x, side="left") - 1 clipped to [0, n-2]  (jax RegularGridInterpolator._find_indices)
 template <typename T>
-EX_HD int lut_cell(const T *g, int n, T inv_d, T x) {
+EX_HD int lut_cell(const T *g, int n, T inv_d, T x, int regular) {
   T gf = (x - g[0]) * inv_d;
   int i = (gf > (T)0) ? ((gf < (T)(n - 2)) ? (int)gf : n - 2) : 0;
+  if (regular) {  // the guess is the cell or a neighbour: two predicated corrections, no divergent loop
+    i -= (i > 0 && !(g[i] < x)) ? 1 : 0;
+    i += (i < n - 2 && g[i + 1] < x) ? 1 : 0;
+    return i;
+  }
   while (i > 0 && !(g[i] < x)) --i;
   while (i < n - 2 && g[i + 1] < x) ++i;
   return i;
@@ -36,10 +71,21 @@ EX_HD int lut_cell(const T *g, int n, T inv_d, T x) {
 
 template <typename T, int FIRST, int COUNT>
 EX_HD void lut_eval(const LutView<T> &L, T id, T iq, T *out) {
-  const int i = lut_cell<T>(L.gx, L.nx, L.inv_dx, id);
-  const int j = lut_cell<T>(L.gy, L.ny, L.inv_dy, iq);
-  const T yi = (id - L.gx[i]) / (L.gx[i + 1] - L.gx[i]);
-  const T yj = (iq - L.gy[j]) / (L.gy[j + 1] - L.gy[j]);
+  const int i = lut_cell<T>(L.gx, L.nx, L.inv_dx, id, L.regular);
+  const int j = lut_cell<T>(L.gy, L.ny, L.inv_dy, iq, L.regular);
+  T yi, yj;
+  if (L.wx) {
+    InvDiv<T> di, dj;
+    di.d = L.wx[2 * i];
+    di.r = L.wx[2 * i + 1];
+    dj.d = L.wy[2 * j];
+    dj.r = L.wy[2 * j + 1];
+    yi = div_inv<true, T>(id - L.gx[i], di);
+    yj = div_inv<true, T>(iq - L.gy[j], dj);
+  } else {
+    yi = (id - L.gx[i]) / (L.gx[i + 1] - L.gx[i]);
+    yj = (iq - L.gy[j]) / (L.gy[j + 1] - L.gy[j]);
+  }
   const T w00 = ((T)1 - yi) * ((T)1 - yj);
   const T w01 = ((T)1 - yi) * yj;
   const T w10 = yi * ((T)1 - yj);
@@ -317,17 +363,22 @@ EX_HD void pmsm_clip(T a0, T a1, T eps, T omega_el, T u_dc, T adv, const T *an, 
   ud = ud * sc;
   uq = uq * sc;
   T ea = eps + adv * omega_el;
-  ea = pymod<T>(ea, Cst<T>::two_pi());
+  ea = pymod_two_pi<T>(ea);
   if (ea > Cst<T>::pi()) ea = ea + (T)-2 * Cst<T>::pi();
-  T sm, cm;
-  Mth<T>::sincos(-ea, &sm, &cm);
+  // t_dq_alpha_beta(-eps) and, further down, t_dq_alpha_beta(eps): one sincos serves both (sin is odd, cos even)
+  T sp, cp;
+  Mth<T>::sincos(ea, &sp, &cp);
+  const T sm = -sp, cm = cp;
   const T ua = cm * ud + sm * uq;
   const T ub = -sm * ud + cm * uq;
-  const T ang = Mth<T>::atan2(ub, ua);
-  const T third = (T)(2.0 / 3.0 * 3.141592653589793);
-  const int i0 = Mth<T>::sin(ang - third * (T)0) >= (T)0;
-  const int i1 = Mth<T>::sin(ang - third * (T)1) >= (T)0;
-  const int i2 = Mth<T>::sin(ang - third * (T)2) >= (T)0;
+  // sector bits i_k = [sin(angle(u) - k * 2 pi / 3) >= 0] (pmsm_env.py:92-96).  sin(angle(u) - phi) has the sign of
+  // ub * cos(phi) - ua * sin(phi), so the three bits are half-plane tests on (ua, ub) -- no atan2, no sine.  Only
+  // vectors within rounding distance of a sector boundary can land in the neighbouring sector, where the clipped
+  // result is the same up to rounding (the limit is continuous across sectors).
+  const T r3 = Mth<T>::sqrt((T)3);
+  const int i0 = ub >= (T)0;
+  const int i1 = ub + r3 * ua <= (T)0;
+  const int i2 = r3 * ua - ub >= (T)0;
   const T H = (T)0.5f, S3 = (T)0.8660254037844386f;
   T rr = (T)1, ri = (T)0;
   const int code = (i0 << 2) | (i1 << 1) | i2;
@@ -338,12 +389,10 @@ EX_HD void pmsm_clip(T a0, T a1, T eps, T omega_el, T u_dc, T adv, const T *an, 
   else if (code == 1) { rr = -H; ri = S3; }
   T zr = ua * rr - ub * ri, zi = ua * ri + ub * rr;
   const T lim_r = (T)(2.0 / 3.0);
-  const T lim_i = (T)(2.0 / 3.0) * Mth<T>::sqrt((T)3);
+  const T lim_i = (T)(2.0 / 3.0) * r3;
   zr = zr < -lim_r ? -lim_r : (zr > lim_r ? lim_r : zr);
   zi = zi < (T)0 ? (T)0 : (zi > lim_i ? lim_i : zi);
   const T wr = zr * rr - zi * (-ri), wi = zr * (-ri) + zi * rr;
-  T sp, cp;
-  Mth<T>::sincos(ea, &sp, &cp);
   const T vd = cp * wr + sp * wi;
   const T vq = -sp * wr + cp * wi;
   *ud_out = vd * half_dc;

@@ -46,9 +46,10 @@ struct SimSchedule {
 };
 
 struct DevLut {
-  void *blob = nullptr;  // [gx | gy | cells] in the plan dtype, 16-byte padded sections
-  size_t bytes = 0, off_gy = 0, off_cells = 0;
+  void *blob = nullptr;  // [gx | gy | cells | wx | wy] in the plan dtype, 16-byte padded sections
+  size_t bytes = 0, off_gy = 0, off_cells = 0, off_wx = 0, off_wy = 0;
   int nx = 0, ny = 0;
+  int regular = 0;       // both grids equidistant up to rounding (cell guess at most one off)
   double inv_dx = 0, inv_dy = 0;
 };
 

@@ -34,18 +34,24 @@ inline KParams<T> make_kparams(const ExenvPlan &plan) {
 }
 
 template <typename T>
+inline LutGeom<T> make_lut_geom(const ExenvPlan &plan) {
+  LutGeom<T> g{};
+  g.bytes = (unsigned)plan.lut.bytes;
+  g.off_gy = (unsigned)plan.lut.off_gy;
+  g.off_cells = (unsigned)plan.lut.off_cells;
+  g.off_wx = (unsigned)plan.lut.off_wx;
+  g.off_wy = (unsigned)plan.lut.off_wy;
+  g.nx = plan.lut.nx;
+  g.ny = plan.lut.ny;
+  g.regular = plan.lut.regular;
+  g.inv_dx = (T)plan.lut.inv_dx;
+  g.inv_dy = (T)plan.lut.inv_dy;
+  return g;
+}
+template <typename T>
 inline LutView<T> make_lut_view(const ExenvPlan &plan) {
   LutView<T> L{};
-  if (plan.lut.blob) {
-    const char *b = (const char *)plan.lut.blob;
-    L.gx = (const T *)b;
-    L.gy = (const T *)(b + plan.lut.off_gy);
-    L.cells = (const T *)(b + plan.lut.off_cells);
-    L.nx = plan.lut.nx;
-    L.ny = plan.lut.ny;
-    L.inv_dx = (T)plan.lut.inv_dx;
-    L.inv_dy = (T)plan.lut.inv_dy;
-  }
+  if (plan.lut.blob) L = lut_view_at<T>(plan.lut.blob, make_lut_geom<T>(plan));
   return L;
 }
 

@@ -102,11 +102,51 @@ EX_HD T norm_inv(T x, T mn, const InvDiv<T> &span) {
   return div_inv<FAST, T>((T)2 * (x - mn), span) - (T)1;
 }
 
+// C fmod(x, y) for y > 0, exactly, without libm's iterative reduction when the quotient is moderate (angles: a few
+// turns at most).  q' = trunc(RN(|x| * RN(1/y)) * (1 + 2^-21)) is the true integer quotient q or q + 1 (the upward bias
+// beats the two roundings of the product; it needs |x| / y < 2^20); |x| - q' * y is then a multiple of ulp(y) of
+// magnitude below y, so the FMA delivers it exactly, and so does the single correction r + y.  The sign of x is
+// restored last (fmod(-2 pi, 2 pi) = -0.0).  Larger quotients take libm.
+template <typename T>
+struct FmodK;
+template <>
+struct FmodK<float> {
+  static constexpr float BIAS = 1.000000476837158203125f;  // 1 + 2^-21
+  static constexpr float QMAX = 1048576.0f;                  // 2^20
+};
+template <>
+struct FmodK<double> {
+  static constexpr double BIAS = 1.0 + 8.8817841970012523e-16;  // 1 + 2^-50
+  static constexpr double QMAX = 562949953421312.0;              // 2^49
+};
+EX_HD float trunc_(float x) { return ::truncf(x); }
+EX_HD double trunc_(double x) { return ::trunc(x); }
+EX_HD float copysign_(float x, float s) { return ::copysignf(x, s); }
+EX_HD double copysign_(double x, double s) { return ::copysign(x, s); }
+template <typename T>
+EX_HD T fmod_pos(T x, T y, T inv_y) {
+  const T ax = Mth<T>::abs(x);
+  if (!(ax < FmodK<T>::QMAX * y)) return Mth<T>::fmod(x, y);  // huge, inf or nan
+  if (ax < y) return x;
+  const T q = trunc_(ax * inv_y * FmodK<T>::BIAS);
+  T r = fma_(-q, y, ax);
+  if (r < (T)0) r += y;
+  return copysign_(r, x);
+}
+
 // jnp `%`: C fmod followed by the sign correction (jax.numpy.remainder); SURVEY Appendix A.
 template <typename T>
 EX_HD T pymod(T x, T y) {
   T r = Mth<T>::fmod(x, y);
   if (r != (T)0 && ((r < (T)0) != (y < (T)0))) r += y;
+  return r;
+}
+// pymod(x, 2 pi) through fmod_pos (identical values)
+template <typename T>
+EX_HD T pymod_two_pi(T x) {
+  const T y = (T)(2 * 3.141592653589793);
+  T r = fmod_pos<T>(x, y, (T)1 / y);
+  if (r < (T)0) r += y;
   return r;
 }
 
@@ -122,7 +162,7 @@ struct Cst {
 // pmsm_env.py:571)
 template <typename T>
 EX_HD T wrap_pi(T th) {
-  return pymod<T>(th + Cst<T>::pi(), Cst<T>::two_pi()) - Cst<T>::pi();
+  return pymod_two_pi<T>(th + Cst<T>::pi()) - Cst<T>::pi();
 }
 
 template <typename T>

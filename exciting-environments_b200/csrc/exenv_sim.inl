@@ -62,10 +62,8 @@ struct SimK {
   int control[EXENV_MAX_CONTROL];
   int deadtime;
   T pmsm_adv, pmsm_lin_stop;  // (deadtime+0.5)*tau ; tau*(T-1) = linspace stop of pmsm_env.py:721
-  unsigned lut_bytes, lut_off_gy, lut_off_cells;
   const void *lut_blob;
-  int lut_nx, lut_ny;
-  T lut_inv_dx, lut_inv_dy;
+  LutGeom<T> lut;
 };
 
 // bytes of the per-tile schedule slice in shared memory (records, words, step lengths), 16-byte aligned
@@ -457,13 +455,13 @@ __global__ void __launch_bounds__(SIM_E)
     // stage the flux maps once per CTA: TMA bulk copy + mbarrier
     size_t off = (sim_sched_bytes<T>(a.step_cap, a.save_cap) + (act_elems + (size_t)a.save_cap * NST * SIM_EP) * sizeof(T) + 15) & ~(size_t)15;
     unsigned char *sm_lut = smem_raw + off;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut_bytes);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut.bytes);
     if (e == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(a.lut_bytes)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(a.lut.bytes)
                    : "memory");
-      tma_bulk_load(sm_lut, a.lut_blob, a.lut_bytes, mbar);
+      tma_bulk_load(sm_lut, a.lut_blob, a.lut.bytes, mbar);
     }
     __syncthreads();
     {
@@ -476,13 +474,7 @@ __global__ void __launch_bounds__(SIM_E)
             : "memory");
       }
     }
-    aux.lut.gx = reinterpret_cast<const T *>(sm_lut);
-    aux.lut.gy = reinterpret_cast<const T *>(sm_lut + a.lut_off_gy);
-    aux.lut.cells = reinterpret_cast<const T *>(sm_lut + a.lut_off_cells);
-    aux.lut.nx = a.lut_nx;
-    aux.lut.ny = a.lut_ny;
-    aux.lut.inv_dx = a.lut_inv_dx;
-    aux.lut.inv_dy = a.lut_inv_dy;
+    aux.lut = lut_view_at<T>(sm_lut, a.lut);
   }
 
   // ---- per-environment constants and initial state
@@ -673,14 +665,8 @@ static int launch_sim_t(const ExenvPlan &plan, const ExenvSimArgs &x, const SimS
   a.deadtime = plan.deadtime;
   a.pmsm_adv = (T)plan.pmsm_adv;
   a.pmsm_lin_stop = (T)(plan.desc.tau * (double)(x.n_actions - 1));
-  a.lut_bytes = (unsigned)plan.lut.bytes;
-  a.lut_off_gy = (unsigned)plan.lut.off_gy;
-  a.lut_off_cells = (unsigned)plan.lut.off_cells;
   a.lut_blob = plan.lut.blob;
-  a.lut_nx = plan.lut.nx;
-  a.lut_ny = plan.lut.ny;
-  a.lut_inv_dx = (T)plan.lut.inv_dx;
-  a.lut_inv_dy = (T)plan.lut.inv_dy;
+  a.lut = make_lut_geom<T>(plan);
   KParams<T> kp = make_kparams<T>(plan);
   const size_t smem = smem_bytes_t<Env, T>(plan, sch.act_cap, sch.save_cap, sch.tile_steps);
   auto kern = sim_kernel<Env, SOLVER, T, PER_ENV>;

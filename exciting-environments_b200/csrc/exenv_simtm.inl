@@ -50,10 +50,8 @@ struct SimTmK {
   int control[EXENV_MAX_CONTROL];
   int deadtime;
   T pmsm_adv, pmsm_lin_stop;
-  unsigned lut_bytes, lut_off_gy, lut_off_cells;
   const void *lut_blob;
-  int lut_nx, lut_ny;
-  T lut_inv_dx, lut_inv_dy;
+  LutGeom<T> lut;
 };
 
 __device__ __forceinline__ unsigned tm_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -260,15 +258,15 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   if constexpr (Env::IS_PMSM && Env::SATURATED) {
     // stage the flux maps once per CTA: TMA bulk copy + mbarrier (SASS: UBLKCP)
     unsigned char *sm_lut = smem_raw;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut_bytes);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm_lut + a.lut.bytes);
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tm_smem_u32(mbar)));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tm_smem_u32(mbar)), "r"(a.lut_bytes)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tm_smem_u32(mbar)), "r"(a.lut.bytes)
                    : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                        tm_smem_u32(sm_lut)),
-                   "l"(a.lut_blob), "r"(a.lut_bytes), "r"(tm_smem_u32(mbar))
+                   "l"(a.lut_blob), "r"(a.lut.bytes), "r"(tm_smem_u32(mbar))
                    : "memory");
     }
     __syncthreads();
@@ -282,13 +280,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      aux[v].lut.gx = reinterpret_cast<const T *>(sm_lut);
-      aux[v].lut.gy = reinterpret_cast<const T *>(sm_lut + a.lut_off_gy);
-      aux[v].lut.cells = reinterpret_cast<const T *>(sm_lut + a.lut_off_cells);
-      aux[v].lut.nx = a.lut_nx;
-      aux[v].lut.ny = a.lut_ny;
-      aux[v].lut.inv_dx = a.lut_inv_dx;
-      aux[v].lut.inv_dy = a.lut_inv_dy;
+      aux[v].lut = lut_view_at<T>(sm_lut, a.lut);
     }
   }
   if (!valid) return;  // no block-wide synchronisation below
@@ -668,14 +660,8 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   a.deadtime = plan.deadtime;
   a.pmsm_adv = (T)plan.pmsm_adv;
   a.pmsm_lin_stop = (T)(plan.desc.tau * (double)(x.n_actions - 1));
-  a.lut_bytes = (unsigned)plan.lut.bytes;
-  a.lut_off_gy = (unsigned)plan.lut.off_gy;
-  a.lut_off_cells = (unsigned)plan.lut.off_cells;
   a.lut_blob = plan.lut.blob;
-  a.lut_nx = plan.lut.nx;
-  a.lut_ny = plan.lut.ny;
-  a.lut_inv_dx = (T)plan.lut.inv_dx;
-  a.lut_inv_dy = (T)plan.lut.inv_dy;
+  a.lut = make_lut_geom<T>(plan);
   KParams<T> kp = make_kparams<T>(plan);
   size_t smem = 0;
   if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = plan.lut.bytes + 16;

@@ -155,4 +155,18 @@ void hc_sim(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, long n
   if (d->dtype == EXENV_F64) sim_any<double>(d, lut, B, n_actions, n_save, n_steps, words, dts, thetas, sin, actions, traj);
   else sim_any<float>(d, lut, B, n_actions, n_save, n_steps, words, dts, thetas, sin, actions, traj);
 }
+// exenv_math.cuh: fmod_pos (exact C fmod without the iterative reduction) and wrap_pi on arrays
+void hc_fmod_two_pi(long n, int is_f64, const void *x, void *fmod_out, void *wrap_out) {
+  for (long i = 0; i < n; ++i) {
+    if (is_f64) {
+      const double y = 2 * 3.141592653589793;
+      ((double *)fmod_out)[i] = fmod_pos<double>(((const double *)x)[i], y, 1.0 / y);
+      ((double *)wrap_out)[i] = wrap_pi<double>(((const double *)x)[i]);
+    } else {
+      const float y = (float)(2 * 3.141592653589793);
+      ((float *)fmod_out)[i] = fmod_pos<float>(((const float *)x)[i], y, 1.0f / y);
+      ((float *)wrap_out)[i] = wrap_pi<float>(((const float *)x)[i]);
+    }
+  }
+}
 }

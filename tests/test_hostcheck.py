@@ -132,3 +132,28 @@ def test_schedule_exposes_zoh_lag_and_fp32_drift():
     assert info.n_save == 2001
     assert np.all((theta >= 0) & (theta <= 1))
     assert tiles[:, 1].sum() == info.n_steps and tiles[:, 5].sum() == info.n_save
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fast_fmod_is_exact(hostcheck_lib, dtype):
+    """exenv_math.cuh fmod_pos / wrap_pi: bit-identical to C fmod (numpy.fmod) and to the reference's
+    ((theta + pi) % (2 pi)) - pi, including multiples of 2 pi, signed zeros, huge arguments, inf and nan."""
+    rng = np.random.default_rng(0)
+    two_pi = dtype(2 * np.pi)
+    k = np.arange(-40, 41).astype(dtype)
+    edge = np.concatenate([k * two_pi, np.nextafter(k * two_pi, dtype(np.inf)), np.nextafter(k * two_pi, dtype(-np.inf)),
+                           np.array([0.0, -0.0, 1e-30, -1e-30, 3e7, -3e7, 1e20, -1e20, np.inf, -np.inf, np.nan], dtype)])
+    x = np.concatenate([edge, rng.uniform(-50, 50, 200000).astype(dtype), rng.uniform(-7, 7, 200000).astype(dtype),
+                        (rng.standard_normal(50000) * 1e5).astype(dtype)])
+    f, w = np.empty_like(x), np.empty_like(x)
+    hostcheck_lib.hc_fmod_two_pi(C.c_long(x.size), C.c_int(dtype == np.float64), C.c_void_p(x.ctypes.data),
+                                 C.c_void_p(f.ctypes.data), C.c_void_p(w.ctypes.data))
+    with np.errstate(invalid="ignore"):
+        ref = np.fmod(x, two_pi)
+        pi = dtype(np.pi)
+        wref = np.mod(x + pi, two_pi) - pi
+    u = np.uint32 if dtype == np.float32 else np.uint64
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(f), nan) and np.array_equal(f[~nan].view(u), ref[~nan].view(u))
+    nanw = np.isnan(wref)
+    assert np.array_equal(np.isnan(w), nanw) and np.array_equal(w[~nanw], wref[~nanw])
