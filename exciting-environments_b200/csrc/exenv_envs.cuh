@@ -380,13 +380,12 @@ EX_HD void pmsm_clip(T a0, T a1, T eps, T omega_el, T u_dc, T adv, const T *an, 
   const int i1 = ub + r3 * ua <= (T)0;
   const int i2 = r3 * ua - ub >= (T)0;
   const T H = (T)0.5f, S3 = (T)0.8660254037844386f;
-  T rr = (T)1, ri = (T)0;
+  // ROTATION_MAP[i0, i1, i2] (pmsm_env.py:37-43) as selects: neighbouring lanes sit in different sectors, a branch
+  // per sector would serialise the warp
   const int code = (i0 << 2) | (i1 << 1) | i2;
-  if (code == 5) { rr = H; ri = S3; }
-  else if (code == 6) { rr = H; ri = -S3; }
-  else if (code == 2) { rr = -H; ri = -S3; }
-  else if (code == 3) { rr = (T)-1; ri = (T)0; }
-  else if (code == 1) { rr = -H; ri = S3; }
+  const bool c1 = code == 1, c2 = code == 2, c3 = code == 3, c5 = code == 5, c6 = code == 6;
+  const T rr = (c5 || c6) ? H : ((c1 || c2) ? -H : (c3 ? (T)-1 : (T)1));
+  const T ri = (c5 || c1) ? S3 : ((c6 || c2) ? -S3 : (T)0);
   T zr = ua * rr - ub * ri, zi = ua * ri + ub * rr;
   const T lim_r = (T)(2.0 / 3.0);
   const T lim_i = (T)(2.0 / 3.0) * r3;

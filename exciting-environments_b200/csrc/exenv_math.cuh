@@ -127,7 +127,7 @@ template <typename T>
 EX_HD T fmod_pos(T x, T y, T inv_y) {
   const T ax = Mth<T>::abs(x);
   if (!(ax < FmodK<T>::QMAX * y)) return Mth<T>::fmod(x, y);  // huge, inf or nan
-  if (ax < y) return x;
+  // no shortcut for |x| < y: q is 0 or 1 there and the same two exact operations return |x| (branch-free)
   const T q = trunc_(ax * inv_y * FmodK<T>::BIAS);
   T r = fma_(-q, y, ax);
   if (r < (T)0) r += y;
