@@ -187,6 +187,8 @@ def run_b200(args):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # its banner goes to stdout, next to the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     env = ex.MassSpringDamper(batch_size=B, solver=ex.Tsit5(), tau=TAU, dtype=torch.float32, device=dev)
