@@ -317,3 +317,61 @@ def test_time_major_equals_batch_major(excenvs, env, solver):
         assert traj_err(x2, x1, sc) <= 2e-6, name
         assert np.array_equal(np_(getattr(l2.physical_state, name)), x2[:, -1])
     assert np.max(np.abs(np_(o1) - np_(o2))) <= 1e-5
+
+
+@pytest.mark.parametrize("env,solver", [("mass_spring_damper", O.TSIT5), ("pendulum", O.EULER), ("cart_pole", O.TSIT5),
+                                        ("fluid_tank", O.TSIT5)])
+def test_time_major_envs_per_thread_and_fallbacks(excenvs, env, solver):
+    """Time-major kernel: 1, 2 or 4 environments per thread (vector accesses) give bit-identical trajectories; a batch
+    that does not split evenly falls back to narrower vectors; the fused-epilogue flavour matches the plain one."""
+    rng = np.random.default_rng(23)
+    orc = O.Oracle(env, solver=solver, dtype=np.float32)
+    for B in (4 * 97, 4 * 97 + 2, 4 * 97 + 1):  # V = 4 / 2 / 1 at most
+        T = 150
+        st = random_state(orc, B, rng, spread=0.5)
+        acts = torch.as_tensor(rng.uniform(-1, 1, (B, T, orc.A)).astype(np.float32), device="cuda")
+        e = make_env(excenvs, orc, B)
+        base = e.vmap_sim_ahead(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major", block_envs=1)
+        for v in (0, 2, 4):
+            other = e.vmap_sim_ahead(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major", block_envs=v)
+            assert torch.equal(base[0], other[0]), (B, v)
+            for name in e.PHYS_FIELDS:
+                assert torch.equal(getattr(base[1].physical_state, name), getattr(other[1].physical_state, name))
+                assert torch.equal(getattr(base[2].physical_state, name), getattr(other[2].physical_state, name))
+        full = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major")
+        assert torch.equal(base[0], full[0])
+        bm = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau)
+        assert torch.equal(full[4], bm[4]) and torch.equal(full[5], bm[5]) and torch.equal(full[3], bm[3])
+        assert full[3].shape == (B, T, 1) and full[4].shape == (B, T + 1, orc.n_trunc) and full[5].shape == (B, T, 1)
+
+
+def test_time_major_c_abi_misaligned_and_partial_outputs(excenvs):
+    """Raw C-ABI call in the time-major layout with buffers that rule out vector accesses (4-byte aligned only) and with
+    a skipped trajectory leaf: the generic instantiation must give the same values as the vectorised one."""
+    import ctypes as C
+
+    L = excenvs._lib
+    B, T = 256, 64
+    e = excenvs.MassSpringDamper(batch_size=B, solver=excenvs.Tsit5(), dtype=torch.float32)
+    _, s = e.vmap_reset(rng=3)
+    acts = torch.rand((T, B, 1), device="cuda") * 2 - 1
+    obs_ref, states_ref, _ = e.vmap_sim_ahead(s, acts.permute(1, 0, 2), e.tau, e.tau, layout="time_major")
+    pad = 1  # one float off a 16-byte boundary
+    a_buf = torch.empty(T * B + pad, device="cuda")
+    a_buf[pad:] = acts.reshape(-1)
+    o_buf = torch.empty((T + 1) * B * 2 + pad, device="cuda")
+    t_buf = torch.empty((T + 1) * B + pad, device="cuda")
+    a = L.ExenvSimArgs()
+    a.batch, a.n_actions, a.obs_stepsize, a.action_stepsize, a.max_steps = B, T, e.tau, e.tau, 4096
+    a.layout = L.LAYOUT_TIME_MAJOR
+    leaves = [getattr(s.physical_state, n).contiguous() for n in e.PHYS_FIELDS]
+    for i in range(2):
+        a.state_in[i] = leaves[i].data_ptr()
+    a.traj[1] = t_buf.data_ptr() + 4 * pad  # leaf 0 skipped (NULL)
+    a.actions, a.obs = a_buf.data_ptr() + 4 * pad, o_buf.data_ptr() + 4 * pad
+    L.check(L.lib().exenv_sim_ahead(e._plan().handle, C.byref(a), e._stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(o_buf[pad:].reshape(T + 1, B, 2).permute(1, 0, 2), obs_ref)
+    assert torch.equal(t_buf[pad:].reshape(T + 1, B).t(), states_ref.physical_state.velocity)
+    a.layout = 7
+    assert L.lib().exenv_sim_ahead(e._plan().handle, C.byref(a), e._stream()) == -1  # EXENV_ERR_INVALID
