@@ -717,6 +717,9 @@ static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const
   int v = x.block_envs > 0 ? x.block_envs : simtm_auto_v<Env, SOLVER, T>();
   if (v > VMAX) v = VMAX;
   if (v == 3) v = 2;
+  // small batches: threads first (one 148-SM wave of 1024 threads per SM), environments per thread second
+  if (x.block_envs <= 0)
+    while (v > 1 && x.batch / v < 148L * 1024) v >>= 1;
   // V consecutive environments per thread move as one vector: the batch must split evenly and every buffer must be
   // aligned to the vector (at most 16 bytes per access)
   auto ok = [&](int vv) {
