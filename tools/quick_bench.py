@@ -165,3 +165,9 @@ if __name__ == "__main__":
         print(json.dumps(dict(kind="config1", B=B, N=N, us_per_step_eager=t_eager * 1e6, us_per_step_graph=t_graph * 1e6,
                               us_per_step_sim_ahead=t_sim * 1e6, env_steps_per_s_eager=B / t_eager,
                               env_steps_per_s_graph=B / t_graph, env_steps_per_s_sim_ahead=B / t_sim)), flush=True)
+    if what in ("all", "sweep_step"):  # BASELINE configs[4]: batch-size sweep of vmap_step, all six envs
+        for name, cls in (("pendulum", ex.Pendulum), ("msd", ex.MassSpringDamper), ("tank", ex.FluidTank),
+                          ("cartpole", ex.CartPole), ("acrobot", ex.Acrobot), ("pmsm", ex.PMSM)):
+            for solver in (ex.Euler(), ex.Tsit5()):
+                for lb in range(10, 29, 2):
+                    bench_step(name, cls, solver, f32, 1 << lb)
