@@ -54,8 +54,12 @@ static ffi::Error StepImpl(cudaStream_t stream, ffi::RemainingArgs args, ffi::Re
 //                 rets = observations (B, N+1, O') + D trajectory leaves (B, N+1) + D last-state leaves (+ NODE k_last)
 static ffi::Error SimAheadImpl(cudaStream_t stream, ffi::RemainingArgs args, ffi::RemainingRets rets, int64_t plan,
                                int64_t n_phys, int64_t n_ode, int64_t n_control, double obs_stepsize,
-                               double action_stepsize, int64_t max_steps) {
+                               double action_stepsize, int64_t max_steps, int64_t layout) {
+  // `layout` = ExenvLayout.  XLA always reports the LOGICAL dimensions (B, T, A); with EXENV_LAYOUT_TIME_MAJOR the
+  // caller has declared the physical layouts on the custom call (jax_ffi.py: input_layouts / output_layouts), so the
+  // buffers behind these pointers are (T, B, A), (N+1, B, O'), (N+1, B).
   ExenvSimArgs a = {};
+  a.layout = (int32_t)layout;
   auto acts = args.get<ffi::AnyBuffer>(n_phys);
   if (!acts.has_value()) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "missing actions");
   a.batch = acts->dimensions()[0];
@@ -99,5 +103,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(ExenvSimAheadFfi, SimAheadImpl,
                                   .Attr<int64_t>("n_control")
                                   .Attr<double>("obs_stepsize")
                                   .Attr<double>("action_stepsize")
-                                  .Attr<int64_t>("max_steps"));
+                                  .Attr<int64_t>("max_steps")
+                                  .Attr<int64_t>("layout"));
 #endif  // EXENV_HAVE_XLA_FFI

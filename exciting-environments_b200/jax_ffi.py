@@ -46,8 +46,13 @@ def ffi_vmap_step(env, plan_handle: int, state_leaves, action, ref_leaves=()):
     return res[0], res[1:1 + D], res[1 + D:]
 
 
-def ffi_vmap_sim_ahead(env, plan_handle: int, state_leaves, actions, obs_stepsize, action_stepsize, ref_leaves=()):
-    """`CoreEnvironment.vmap_sim_ahead` as one custom call: (observations, trajectory leaves, last leaves, k_last)."""
+def ffi_vmap_sim_ahead(env, plan_handle: int, state_leaves, actions, obs_stepsize, action_stepsize, ref_leaves=(),
+                       layout="time_major"):
+    """`CoreEnvironment.vmap_sim_ahead` as one custom call: (observations, trajectory leaves, last leaves, k_last).
+
+    ``layout="time_major"`` declares the physical layouts of the trajectory operands on the custom call (major-to-minor
+    axis orders): the arrays keep the reference's logical shapes, XLA relayouts only where a consumer needs the default
+    layout.  [recall of the public jax.ffi API -- unverified in this image]"""
     import jax
 
     B, T, dt = actions.shape[0], actions.shape[1], actions.dtype
@@ -55,8 +60,13 @@ def ffi_vmap_sim_ahead(env, plan_handle: int, state_leaves, actions, obs_stepsiz
     ns = 1 + int(action_stepsize * T / obs_stepsize)
     outs = ([jax.ShapeDtypeStruct((B, ns, env.obs_dim), dt)] + [jax.ShapeDtypeStruct((B, ns), dt)] * D
             + [jax.ShapeDtypeStruct((B,), dt)] * (D + node))
-    res = jax.ffi.ffi_call("exenv_sim_ahead", outs, vmap_method="sequential")(
+    tm = layout == "time_major"
+    kw = {}
+    if tm:
+        kw = dict(input_layouts=[None] * D + [(1, 0, 2)] + [None] * len(ref_leaves),
+                  output_layouts=[(1, 0, 2)] + [(1, 0)] * D + [None] * (D + node))
+    res = jax.ffi.ffi_call("exenv_sim_ahead", outs, vmap_method="sequential", **kw)(
         *state_leaves, actions, *ref_leaves, plan=int(plan_handle), n_phys=D, n_ode=node,
         n_control=len(env.control_state), obs_stepsize=float(obs_stepsize), action_stepsize=float(action_stepsize),
-        max_steps=int(env.max_steps or 0))
+        max_steps=int(env.max_steps or 0), layout=_lib.LAYOUT_TIME_MAJOR if tm else _lib.LAYOUT_BATCH_MAJOR)
     return res[0], res[1:1 + D], res[1 + D:1 + 2 * D], res[1 + 2 * D:]
