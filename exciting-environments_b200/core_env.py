@@ -149,10 +149,18 @@ class CoreEnvironment:
             if not torch.cuda.is_available():
                 raise RuntimeError("exciting-environments_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
             self._device = torch.device("cuda", torch.cuda.current_device())
+        elif self._device.index is None:  # "cuda" -> "cuda:<current>" (tensor.device always carries the index)
+            self._device = torch.device(self._device.type, torch.cuda.current_device())
         return self._device
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        """The caller's current CUDA stream as a raw ``cudaStream_t`` (the C call is a few hundred ns; the public
+        ``torch.cuda.current_stream`` wrapper costs several microseconds per control step)."""
+        dev = self.device
+        try:
+            return C.c_void_p(torch._C._cuda_getCurrentRawStream(dev.index))
+        except AttributeError:  # private API moved: fall back to the public one
+            return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
     @property
     def obs_dim(self):
@@ -226,6 +234,9 @@ class CoreEnvironment:
         return self._const[key]
 
     def _as(self, x, shape=None):
+        if (type(x) is torch.Tensor and x.dtype == self.dtype and x.device == self._device and x.is_contiguous()
+                and (shape is None or x.shape == shape)):
+            return x  # the common case of a step loop: the leaf came out of the previous call
         t = torch.as_tensor(x)
         if t.device != self.device or t.dtype != self.dtype:
             t = t.to(device=self.device, dtype=self.dtype)
@@ -332,7 +343,14 @@ class CoreEnvironment:
         phys_in = self._phys_leaves(state.physical_state, B)
         action = self._as(action, (B, A))
         dev, dt = self.device, self.dtype
-        phys_out = phys_in if inplace else [torch.empty(B, dtype=dt, device=dev) for _ in range(D)]
+        tsit = self._solver_id == _lib.TSIT5
+        # one allocation for the D new leaves (+ the Tsit5 derivative leaves): rows of a (D [+ NODE], B) block
+        rows = (0 if inplace else D) + (NODE if tsit else 0)
+        if rows and (B * phys_in[0].element_size()) % 16 == 0:  # rows stay 16-byte aligned for the vector path
+            block = torch.empty((rows, B), dtype=dt, device=dev).unbind(0)
+        else:
+            block = tuple(torch.empty(B, dtype=dt, device=dev) for _ in range(rows))
+        phys_out = phys_in if inplace else list(block[:D])
         obs = torch.empty((B, self.obs_dim), dtype=dt, device=dev)
         a = _lib.ExenvStepArgs()
         a.batch = B
@@ -346,8 +364,8 @@ class CoreEnvironment:
                 a.ref[i] = refs[i].data_ptr()
         a.action, a.obs = action.data_ptr(), obs.data_ptr()
         kout = None
-        if self._solver_id == _lib.TSIT5:
-            kout = tuple(torch.empty(B, dtype=dt, device=dev) for _ in range(NODE))
+        if tsit:
+            kout = tuple(block[-NODE:])
             for i in range(NODE):
                 a.k_out[i] = kout[i].data_ptr()
         rew = trunc = term = None
@@ -387,8 +405,13 @@ class CoreEnvironment:
             "The action needs to be of shape (batch_size, action_dim) which is "
             + f"{(B, self.action_dim)}, but {shape} is given"
         )
-        leaves = tree_flatten(state.physical_state)[0]
-        ps = (tuple(leaves[0].shape)[0] if is_array(leaves[0]) else 1, len(leaves))
+        phys = state.physical_state
+        if type(phys) is self.PhysicalState:  # field count is fixed by the class: only the batch axis can be wrong
+            first = getattr(phys, self.PHYS_FIELDS[0])
+            ps = (tuple(first.shape)[0] if is_array(first) and len(first.shape) else 1, self.physical_state_dim)
+        else:
+            leaves = tree_flatten(phys)[0]
+            ps = (tuple(leaves[0].shape)[0] if is_array(leaves[0]) else 1, len(leaves))
         assert ps == (B, self.physical_state_dim), (
             "The physical state needs to be of shape (batch_size, physical_state_dim) which is "
             + f"{(B, self.physical_state_dim)}, but {ps} is given"

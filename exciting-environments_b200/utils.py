@@ -43,6 +43,18 @@ def load_sim_properties_from_json(filename):
 
 
 # ---- minimal pytree support (dataclass field order == jax_dataclasses flatten order) ---------------
+_FIELD_NAMES = {}  # class -> dataclass field names (None for non-dataclasses); reflection once per class
+
+
+def _field_names(cls):
+    try:
+        return _FIELD_NAMES[cls]
+    except KeyError:
+        names = tuple(f.name for f in fields(cls)) if is_dataclass(cls) else None
+        _FIELD_NAMES[cls] = names
+        return names
+
+
 def tree_flatten(tree):
     """Leaves in dataclass-field / tuple order; ``None`` is an empty subtree (as in jax.tree_util)."""
     leaves = []
@@ -50,10 +62,15 @@ def tree_flatten(tree):
     def rec(x):
         if x is None:
             return ("none",)
-        if is_dataclass(x) and not isinstance(x, type):
-            return ("dc", type(x), tuple(rec(getattr(x, f.name)) for f in fields(x)))
+        cls = type(x)
+        if cls is tuple or cls is list:
+            return ("seq", cls, tuple(rec(v) for v in x))
+        if cls is not type:
+            names = _field_names(cls)
+            if names is not None:
+                return ("dc", cls, tuple(rec(getattr(x, n)) for n in names))
         if isinstance(x, (tuple, list)):
-            return ("seq", type(x), tuple(rec(v) for v in x))
+            return ("seq", cls, tuple(rec(v) for v in x))
         leaves.append(x)
         return ("leaf",)
 
