@@ -79,8 +79,9 @@ __device__ __forceinline__ void stcs_chunk(void *dst, const void *src) {
     __stcs(reinterpret_cast<unsigned char *>(dst), *reinterpret_cast<const unsigned char *>(src));
   }
 }
-// Loads are volatile asm: the kernel orders them by hand (see the solver loop) and ptxas must neither merge them into
-// wider accesses with dead lanes nor hoist the DRAM-latency action load above the schedule loads.
+// Loads are explicit PTX of the width the kernel wants, in the order the solver loop wants them issued (ptxas is still
+// free to merge and move them; the order below is what keeps it from parking a scoreboard wait behind a DRAM access,
+// see profiles/README.md).
 template <int BYTES, bool NC>
 __device__ __forceinline__ void ld_chunk(void *dst, const void *src) {
   if constexpr (BYTES == 16) {
@@ -110,8 +111,7 @@ template <int BYTES>
 __device__ __forceinline__ void ldcs_chunk(void *dst, const void *src) {
   ld_chunk<BYTES, false>(dst, src);
 }
-// "these values are needed here": an empty volatile asm that consumes them, so that the scoreboard wait for their
-// loads sits at this point of the instruction stream (before the next volatile load is issued).
+// Marks values as used at this point of the program (compiler-level only: it emits no instruction).
 __device__ __forceinline__ void consume_now(unsigned a) { asm volatile("" ::"r"(a)); }
 template <typename T, int N>
 __device__ __forceinline__ void store_vec(T *dst, const T *v) {
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   for (int i = 0; i < n_steps; ++i) {
     const uint64_t w = s_next.w;
     const T dt = s_next.dt;
-    // Load order at the top of a step (all volatile asm, so it is kept): the window slide consumes the action that
+    // Load order at the top of a step: the window slide consumes the action that
     // left for DRAM one step ago; the warp-uniform schedule entries (L1 hits) are loaded and waited for; only then
     // is the next action load issued, so that no scoreboard wait inside the step sits behind a DRAM access.
     slide_to(sched_base(w));
