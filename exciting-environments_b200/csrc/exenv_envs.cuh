@@ -166,6 +166,19 @@ struct MassSpringDamper {
   EX_HD static void post(T *) {}
   EX_HD static bool is_angle(int) { return false; }
   EX_HD static void default_norm_state(T *z) { z[0] = z[1] = (T)0; }  // :261-265
+  template <typename U>
+  using rebind = MassSpringDamper<U>;
+};
+
+// Environments whose right-hand side, post-processing and observation are straight-line +, -, *, fma code can be
+// instantiated with the packed type f32x2 (two environments per value, exenv_math.cuh).
+template <class Env>
+struct env_packable {
+  static constexpr bool value = false;
+};
+template <>
+struct env_packable<MassSpringDamper<float>> {
+  static constexpr bool value = true;
 };
 
 // ---- Fluid tank (fluid_tank/fluid_tank_env.py) ---------------------------------------------------------------

@@ -134,6 +134,56 @@ EX_HD T fmod_pos(T x, T y, T inv_y) {
   return copysign_(r, x);
 }
 
+// ---- two environments per value: sm_100a packed fp32 arithmetic ------------------------------------------------
+// FFMA2 / FMUL2 / FADD2 perform two IEEE fp32 operations per instruction (same results as the scalar instructions, at
+// the same arithmetic rate, for half the issue slots); a scalar operand is broadcast (`R.F32`, immediates and uniform
+// registers included), so shared parameters and solver coefficients stay scalars.  The environment math is written
+// against a scalar type T; instantiating it with f32x2 steps two environments at once.
+struct f32x2 {
+  float x, y;
+  f32x2() = default;
+  EX_HD constexpr f32x2(float s) : x(s), y(s) {}
+  EX_HD constexpr f32x2(double s) : x((float)s), y((float)s) {}
+  EX_HD constexpr f32x2(int s) : x((float)s), y((float)s) {}
+  EX_HD constexpr f32x2(float a, float b) : x(a), y(b) {}
+};
+#if defined(__CUDACC__)
+EX_HD f32x2 operator+(f32x2 a, f32x2 b) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return f32x2(r.x, r.y);
+#else
+  return f32x2(a.x + b.x, a.y + b.y);
+#endif
+}
+EX_HD f32x2 operator-(f32x2 a) { return f32x2(-a.x, -a.y); }
+EX_HD f32x2 operator-(f32x2 a, f32x2 b) { return a + (-b); }
+EX_HD f32x2 operator*(f32x2 a, f32x2 b) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return f32x2(r.x, r.y);
+#else
+  return f32x2(a.x * b.x, a.y * b.y);
+#endif
+}
+EX_HD f32x2 operator/(f32x2 a, f32x2 b) { return f32x2(a.x / b.x, a.y / b.y); }  // set-up code only
+EX_HD f32x2 &operator+=(f32x2 &a, f32x2 b) { return a = a + b; }
+EX_HD f32x2 fma_(f32x2 a, f32x2 b, f32x2 c) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  return f32x2(r.x, r.y);
+#else
+  return f32x2(::fmaf(a.x, b.x, c.x), ::fmaf(a.y, b.y, c.y));
+#endif
+}
+// (z + 1) / 2 * (max - min) + min: the halving as a multiplication (the same value; a packed division would not be
+// strength-reduced by the compiler)
+template <>
+EX_HD f32x2 denorm_mm<f32x2>(f32x2 z, f32x2 mn, f32x2 mx) {
+  return (z + f32x2(1.0f)) * f32x2(0.5f) * (mx - mn) + mn;
+}
+#endif
+
 // jnp `%`: C fmod followed by the sign correction (jax.numpy.remainder); SURVEY Appendix A.
 template <typename T>
 EX_HD T pymod(T x, T y) {

@@ -89,8 +89,8 @@ EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, int dea
 //   rec0 / recs  per-save dense-output records: rec0 = recs[save_idx] (prefetched by the caller one step ahead so its
 //                latency is off the critical path), further saves of the same step read recs[] directly
 // Divisions by parameter-only denominators use the prepared reciprocals (div_inv<true>), see exenv_math.cuh.
-template <class Env, int SOLVER, typename T, class Fetch>
-EX_HD void sim_save_one(const SaveRec<T> &rec, const T *y, const T *y1, const T (*k)[Env::NODE], const T *p,
+template <class Env, int SOLVER, typename T, class Fetch, typename RT>
+EX_HD void sim_save_one(const SaveRec<RT> &rec, const T *y, const T *y1, const T (*k)[Env::NODE], const T *p,
                         typename Env::Aux &aux, long save_idx, Fetch &&fetch, T *st) {
   constexpr int NODE = Env::NODE, A = Env::A;
   T ysv[NODE];
@@ -126,9 +126,11 @@ EX_HD void sim_save_one(const SaveRec<T> &rec, const T *y, const T *y1, const T 
   }
 }
 
-template <class Env, int SOLVER, typename T, class Fetch, class Sink>
+// T is the value type (float, double, or the packed f32x2: two environments per value); the dense-output records are
+// plain scalars of type RT whatever T is.
+template <class Env, int SOLVER, typename T, class Fetch, class Sink, typename RT>
 EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename Env::Pre &pre,
-                        typename Env::Aux &aux, const SaveRec<T> &rec0, const SaveRec<T> *recs, long &save_idx,
+                        typename Env::Aux &aux, const SaveRec<RT> &rec0, const SaveRec<RT> *recs, long &save_idx,
                         Fetch &&fetch, Sink &&sink) {
   constexpr int NODE = Env::NODE, A = Env::A, NST = staged_values<Env>();
   const int base = sched_base(w);
@@ -164,7 +166,7 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
     ++save_idx;
 #pragma unroll 1
     for (int q = 1; q < ns; ++q) {
-      const SaveRec<T> rec = recs[save_idx];
+      const SaveRec<RT> rec = recs[save_idx];
       sim_save_one<Env, SOLVER, T>(rec, y, y1, k, p, aux, save_idx, fetch, st);
       sink(save_idx, st);
       ++save_idx;

@@ -19,7 +19,9 @@
 // step ahead; the per-environment arithmetic is the same exenv_sim_core.cuh code, so both layouts produce identical
 // values.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "exenv_kernel_common.cuh"
 #include "exenv_sim_core.cuh"
@@ -634,8 +636,8 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------------------
-template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
-static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+template <class Env, typename T>
+static SimTmK<T> simtm_args(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch) {
   SimTmK<T> a{};
   a.B = x.batch;
   a.n_actions = x.n_actions;
@@ -662,6 +664,12 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   a.pmsm_lin_stop = (T)(plan.desc.tau * (double)(x.n_actions - 1));
   a.lut_blob = plan.lut.blob;
   a.lut = make_lut_geom<T>(plan);
+  return a;
+}
+
+template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
+static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+  const SimTmK<T> a = simtm_args<Env, T>(plan, x, sch);
   KParams<T> kp = make_kparams<T>(plan);
   size_t smem = 0;
   if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = plan.lut.bytes + 16;
@@ -684,6 +692,29 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   }
   return EXENV_OK;
 }
+
+#ifdef EXENV_SIMTM_PACKED
+#include "exenv_simtm_packed.inl"
+
+// Packed-arithmetic flavour (fp32, env_packable environments, V = 2 or 4).  EXENV_SIMTM_PACKED=0 in the environment
+// selects the scalar kernel (A/B measurements).
+static bool simtm_packed_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("EXENV_SIMTM_PACKED");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <class Env, int SOLVER, int V, bool EPI>
+static int launch_simtm_packed(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+  const SimTmK<float> a = simtm_args<Env, float>(plan, x, sch);
+  const KParams<float> kp = make_kparams<float>(plan);
+  if (sch.win_need <= 2) return launch_simtm_packed_v<Env, SOLVER, 2, V, EPI>(a, kp, x.batch, stream);
+  if (sch.win_need <= 4) return launch_simtm_packed_v<Env, SOLVER, 4, V, EPI>(a, kp, x.batch, stream);
+  set_error("sim_ahead (time-major): a solver step needs %d consecutive actions (> 4)", sch.win_need);
+  return EXENV_ERR_UNSUPPORTED;
+}
+#endif
 
 // Window length: 2 covers every schedule whose steps read at most two consecutive ZOH indices (always the case up to
 // floating-point lag of the accumulated solver time); 4 is the general case (build_schedule_t rejects more).
@@ -739,6 +770,17 @@ static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const
     return r;
   };
   while (v > 1 && !ok(v)) v >>= 1;
+#ifdef EXENV_SIMTM_PACKED
+  if constexpr (std::is_same<T, float>::value && env_packable<Env>::value) {
+    if (simtm_packed_enabled() && (v == 2 || v == 4)) {
+      if (x.reward)
+        return v == 4 ? launch_simtm_packed<Env, SOLVER, 4, true>(plan, x, sch, stream)
+                      : launch_simtm_packed<Env, SOLVER, 2, true>(plan, x, sch, stream);
+      return v == 4 ? launch_simtm_packed<Env, SOLVER, 4, false>(plan, x, sch, stream)
+                    : launch_simtm_packed<Env, SOLVER, 2, false>(plan, x, sch, stream);
+    }
+  }
+#endif
   if (x.reward) {  // fused epilogue (control_state == []): the tuned width or one environment per thread
     constexpr int VA = simtm_auto_v<Env, SOLVER, T>() > VMAX ? VMAX : simtm_auto_v<Env, SOLVER, T>();
     if (v == VA) return launch_simtm_w<Env, SOLVER, T, false, false, VA, true>(plan, x, sch, stream);

@@ -1,0 +1,325 @@
+// exenv_simtm_packed.inl (fp32 only; included inside namespace exenv by exenv_simtm.inl when EXENV_SIMTM_PACKED is set) -- the time-major
+// trajectory kernel with PACKED fp32 arithmetic: a thread owns V = 2 or 4 consecutive environments as V / 2 values of
+// type f32x2, so every solver operation is one FFMA2 / FMUL2 / FADD2 for two environments (exenv_math.cuh).
+//
+// Why: the scalar kernel is bound by instruction issue (profiles/README.md: 178 warp instructions per env-step at
+// 86 % issue-slot utilisation, of which 127 are fp32 arithmetic, while the FMA pipe is 62 % busy).  Packed
+// instructions run at the same arithmetic rate but take half the issue slots, which moves the limit from the
+// schedulers to the FMA pipe itself.  Results are the same IEEE operations in the same order.
+//
+// Scope: environments marked env_packable (straight-line right-hand side: mass-spring-damper), shared parameters,
+// control_state == [], optionally the fused reward / truncated / terminated outputs.  Everything else runs the scalar
+// kernel of exenv_simtm.inl, which this file mirrors step for step.
+template <class Env, int SOLVER, int W, int V, bool EPI>
+__global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
+    simtm_packed_kernel(const __grid_constant__ SimTmK<float> a, const __grid_constant__ KParams<float> kp) {
+  using T = float;
+  using P = f32x2;
+  using EnvP = typename Env::template rebind<P>;
+  static_assert(V % 2 == 0 && !Env::IS_PMSM, "pairs of environments, no PMSM");
+  constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
+  constexpr int NST = staged_values<Env>(), VV = V / 2;
+  constexpr int NT0 = trunc_dim<Env>(0);
+
+  const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;  // first environment of this thread
+  if (b >= a.B) return;
+
+  // shared parameters: scalars (constant bank); the packed copy is a splat the compiler folds into broadcast operands
+  const T *p = kp.v;
+  P pq[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) pq[i] = P(p[i]);
+  const typename EnvP::Pre pre = EnvP::precompute(pq);
+  const P *pn = pq + Env::NSTATIC;
+  typename EnvP::Aux aux{};
+
+  P s0[VV][D], y[VV][NODE], f[VV][NODE], last[VV][NST];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    T tmp[V];
+    load_vec<T, V>(tmp, a.sin[d] + b);
+#pragma unroll
+    for (int vv = 0; vv < VV; ++vv) s0[vv][d] = P(tmp[2 * vv], tmp[2 * vv + 1]);
+  }
+#pragma unroll
+  for (int vv = 0; vv < VV; ++vv) {
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) {
+      y[vv][i] = s0[vv][i];
+      f[vv][i] = P(0.0f);
+    }
+#pragma unroll
+    for (int i = 0; i < NST; ++i) last[vv][i] = P(0.0f);
+  }
+  InvDiv<P> sdiv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<P>(pn[2 * d + 1] - pn[2 * d]);
+
+  // ---- window of prepared ZOH actions (see exenv_simtm.inl) ------------------------------------------------------
+  const int q_max = (int)a.n_actions - 1;
+  TmFetch<P, A, W> win[VV];
+  T pend[V][A];  // raw action of staged index wbase + W, as loaded: it is packed when it is consumed, not before
+  int wbase = 0;
+  const T *ap = a.actions + b * A;
+  int qn = 0;
+  const unsigned act_stride = (unsigned)(a.B * A);
+  constexpr int PF_AHEAD = 6;
+  auto load_next = [&](T (*raw)[A]) {
+    load_vec<T, V * A>(&raw[0][0], ap);
+    if (qn + PF_AHEAD <= q_max) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)PF_AHEAD * act_stride));
+    if (qn < q_max) ap += act_stride;
+    ++qn;
+  };
+  auto prepare = [&](int q, const T (*raw)[A], int k) {
+    q = q < q_max ? q : q_max;
+#pragma unroll
+    for (int vv = 0; vv < VV; ++vv) {
+      P rp[A];
+#pragma unroll
+      for (int c = 0; c < A; ++c) rp[c] = P(raw[2 * vv][c], raw[2 * vv + 1][c]);
+      prepare_action<EnvP, P>((long)q, rp, s0[vv], pq, 0, a.n_actions, P(0.0f), P(0.0f), win[vv].uw[k]);
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    T raw[V][A];
+    load_next(raw);
+    prepare(k, raw, k);
+  }
+  load_next(pend);
+  bool pend_valid = true;
+  auto slide_to = [&](int base) {
+#pragma unroll 1
+    while (wbase < base) {
+      if (!pend_valid) load_next(pend);
+#pragma unroll
+      for (int vv = 0; vv < VV; ++vv)
+#pragma unroll
+        for (int k = 0; k + 1 < W; ++k)
+#pragma unroll
+          for (int c = 0; c < A; ++c) win[vv].uw[k][c] = win[vv].uw[k + 1][c];
+      ++wbase;
+      prepare(wbase + W - 1, pend, W - 1);
+      pend_valid = false;
+    }
+#pragma unroll
+    for (int vv = 0; vv < VV; ++vv) win[vv].wbase = wbase;
+  };
+
+  // ---- saves: stash the step's first save per pair, one vector store per leaf / observation group afterwards -----
+  const unsigned Bu = (unsigned)a.B;
+  T *tp[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) tp[d] = a.traj[d] + b;
+  T *op = a.obs + b * O;
+  T *rwp = EPI ? a.reward + b : nullptr;
+  uint8_t *trp = EPI ? a.trunc + b * NT0 : nullptr;
+  uint8_t *tmp = EPI ? a.term + b : nullptr;
+  P stash[VV][NST];
+  long step_first_save = 0;
+  auto observe_pair = [&](const P *sv, P *ob) {
+#pragma unroll
+    for (int o = 0; o < O; ++o) ob[o] = norm_inv<true, P>(sv[o], pn[2 * o], sdiv[o]);
+  };
+  auto flags_lane = [&](const T *sv, const T *ob, uint8_t *tr, uint8_t &te) {  // control_state == []
+    bool t0 = false;
+#pragma unroll
+    for (int i = 0; i < NT0; ++i) {
+      const bool tv = trunc_entry<Env, T>(i, sv, ob, p);
+      if (i == 0) t0 = tv;
+      tr[i] = tv;
+    }
+    te = terminated_of<Env, T>((T)0, t0);
+  };
+  auto sink_pair = [&](int vv, long sidx, const P *st) {
+#pragma unroll
+    for (int i = 0; i < NST; ++i) last[vv][i] = st[i];
+    if (sidx == step_first_save) {
+#pragma unroll
+      for (int i = 0; i < NST; ++i) stash[vv][i] = st[i];
+    } else {  // rare: a later save of the same step, element-wise
+      P svp[D], obp[O];
+      staged_to_fields<EnvP, P>(st, s0[vv][D - 1], svp);
+      observe_pair(svp, obp);
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const size_t roff = (size_t)(sidx - step_first_save) * Bu + 2 * vv + l;
+        T sv[D], ob[O];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          sv[d] = l ? svp[d].y : svp[d].x;
+          __stcs(tp[d] + roff, sv[d]);
+        }
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+          ob[o] = l ? obp[o].y : obp[o].x;
+          __stcs(op + roff * O + o, ob[o]);
+        }
+        if constexpr (EPI) {
+          uint8_t tr[NT0], te;
+          flags_lane(sv, ob, tr, te);
+#pragma unroll
+          for (int i = 0; i < NT0; ++i) trp[roff * NT0 + i] = tr[i];
+          const size_t r1 = (size_t)(sidx - step_first_save - (step_first_save == 0 ? 1 : 0)) * Bu + 2 * vv + l;
+          __stcs(rwp + r1, (T)0);
+          tmp[r1] = te;
+        }
+      }
+    }
+  };
+  auto flush = [&](int ns) {
+    T sv[V][D], ob[V][O];
+#pragma unroll
+    for (int vv = 0; vv < VV; ++vv) {
+      P svp[D], obp[O];
+      staged_to_fields<EnvP, P>(stash[vv], s0[vv][D - 1], svp);
+      observe_pair(svp, obp);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        sv[2 * vv][d] = svp[d].x;
+        sv[2 * vv + 1][d] = svp[d].y;
+      }
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        ob[2 * vv][o] = obp[o].x;
+        ob[2 * vv + 1][o] = obp[o].y;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      T col[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) col[v] = sv[v][d];
+      store_vec<T, V>(tp[d], col);
+      tp[d] += (size_t)Bu * (unsigned)ns;
+    }
+    store_vec<T, V * O>(op, &ob[0][0]);
+    op += (size_t)Bu * (unsigned)(ns * O);
+    if constexpr (EPI) {
+      uint8_t tr[V][NT0], te[V];
+      T zero[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        flags_lane(sv[v], ob[v], tr[v], te[v]);
+        zero[v] = (T)0;
+      }
+      store_vec<uint8_t, V * NT0>(trp, &tr[0][0]);
+      trp += (size_t)Bu * (unsigned)(ns * NT0);
+      if (step_first_save > 0) {
+        store_vec<T, V>(rwp, zero);
+        store_vec<uint8_t, V>(tmp, te);
+      }
+      const unsigned adv = (unsigned)(step_first_save > 0 ? ns : ns - 1);
+      rwp += (size_t)Bu * adv;
+      tmp += (size_t)Bu * adv;
+    }
+  };
+
+  // ---- the solver loop (same order of loads as the scalar kernel) -----------------------------------------------
+  long save_idx = 0;
+  const StepRec<T> *sp = a.steps;
+  StepRec<T> s_next = load_steprec<T>(sp);
+  slide_to(sched_base(s_next.w));
+  if constexpr (SOLVER == EXENV_TSIT5) {
+#pragma unroll
+    for (int vv = 0; vv < VV; ++vv) sim_first_derivative<EnvP, P>(s_next.w, y[vv], f[vv], pq, pre, aux, win[vv]);
+  }
+  const int n_steps = (int)a.n_steps;
+#pragma unroll 1
+  for (int i = 0; i < n_steps; ++i) {
+    const uint64_t w = s_next.w;
+    const P dt = P(s_next.dt);
+    slide_to(sched_base(w));
+    SaveRec<T> rec;
+    load_saverec<SOLVER, T>(rec, a.recs + save_idx);
+    s_next = load_steprec<T>(++sp);
+    if (!pend_valid) {
+      load_next(pend);
+      pend_valid = true;
+    }
+    step_first_save = save_idx;
+    long si = save_idx;
+    if (W > 2 && SOLVER == EXENV_TSIT5 && sched_dmax(w) <= 1) {
+#pragma unroll
+      for (int vv = 0; vv < VV; ++vv) {
+        si = save_idx;
+        const TmFetchPair<P, A, W> pair{win[vv]};
+        sim_one_step<EnvP, SOLVER, P>(w, dt, y[vv], f[vv], pq, pre, aux, rec, a.recs, si, pair,
+                                      [&](long sidx, const P *st) { sink_pair(vv, sidx, st); });
+      }
+    } else {
+#pragma unroll
+      for (int vv = 0; vv < VV; ++vv) {
+        si = save_idx;
+        sim_one_step<EnvP, SOLVER, P>(w, dt, y[vv], f[vv], pq, pre, aux, rec, a.recs, si, win[vv],
+                                      [&](long sidx, const P *st) { sink_pair(vv, sidx, st); });
+      }
+    }
+    const int ns = sched_saves(w);
+    if (ns > 0) flush(ns);
+    save_idx = si;
+  }
+
+  // ---- last_state and the fresh solver.init derivative at (t1, y_last) --------------------------------------------
+  const int q_last = (int)(a.n_actions - 1);
+  const bool want_k = SOLVER == EXENV_TSIT5 && a.klast[0];
+  if (want_k && q_last > wbase + W - 1) slide_to(q_last - (W - 1));
+  (void)pend_valid;
+  T sl[V][D], fi[V][NODE];
+#pragma unroll
+  for (int vv = 0; vv < VV; ++vv) {
+    P slp[D];
+    staged_to_fields<EnvP, P>(last[vv], s0[vv][D - 1], slp);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      sl[2 * vv][d] = slp[d].x;
+      sl[2 * vv + 1][d] = slp[d].y;
+    }
+    if (want_k) {
+      P u[A], yl[NODE], fp[NODE];
+      win[vv](q_last, u);
+#pragma unroll
+      for (int i = 0; i < NODE; ++i) yl[i] = last[vv][i];
+      EnvP::template rhs<true>(yl, u, pq, pre, aux, fp);
+#pragma unroll
+      for (int i = 0; i < NODE; ++i) {
+        fi[2 * vv][i] = fp[i].x;
+        fi[2 * vv + 1][i] = fp[i].y;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    if (a.last[d]) {
+      T col[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) col[v] = sl[v][d];
+      store_vec<T, V>(a.last[d] + b, col);
+    }
+  if (want_k) {
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) {
+      T col[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) col[v] = fi[v][i];
+      store_vec<T, V>(a.klast[i] + b, col);
+    }
+  }
+}
+
+// Launch (the argument block is the scalar kernel's; the launcher in exenv_simtm.inl has already checked alignment and
+// that the batch splits into groups of V).
+template <class Env, int SOLVER, int W, int V, bool EPI>
+static int launch_simtm_packed_v(const SimTmK<float> &a, const KParams<float> &kp, long batch, cudaStream_t stream) {
+  const long threads = (batch + V - 1) / V;
+  const unsigned grid = (unsigned)((threads + SIMTM_THREADS - 1) / SIMTM_THREADS);
+  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, SIMTM_THREADS, 0, stream>>>(a, kp);
+  g_launch_count++;
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("exenv_sim_ahead (time-major, packed) launch failed: %s", cudaGetErrorString(e));
+    return EXENV_ERR_CUDA;
+  }
+  return EXENV_OK;
+}
+

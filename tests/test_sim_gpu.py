@@ -322,10 +322,21 @@ def test_time_major_equals_batch_major(excenvs, env, solver):
 @pytest.mark.parametrize("env,solver", [("mass_spring_damper", O.TSIT5), ("pendulum", O.EULER), ("cart_pole", O.TSIT5),
                                         ("fluid_tank", O.TSIT5)])
 def test_time_major_envs_per_thread_and_fallbacks(excenvs, env, solver):
-    """Time-major kernel: 1, 2 or 4 environments per thread (vector accesses) give bit-identical trajectories; a batch
-    that does not split evenly falls back to narrower vectors; the fused-epilogue flavour matches the plain one."""
+    """Time-major kernel: 1, 2 or 4 environments per thread (vector accesses) give the same trajectories; a batch
+    that does not split evenly falls back to narrower vectors; the fused-epilogue flavour matches the plain one.
+    Bit-identical for the scalar instantiations; the packed-arithmetic instantiation (fp32 mass-spring-damper with 2 or
+    4 environments per thread: FFMA2) performs the same operations but the compiler may contract a different
+    multiply-add pair, so it is compared to rounding."""
     rng = np.random.default_rng(23)
     orc = O.Oracle(env, solver=solver, dtype=np.float32)
+    packed = env == "mass_spring_damper"
+    scales = field_scales(orc)
+
+    def same(x, y, scale=1.0):
+        if not packed:
+            return torch.equal(x, y)
+        return ((x - y).abs().max() / scale).item() <= 2e-6
+
     for B in (4 * 97, 4 * 97 + 2, 4 * 97 + 1):  # V = 4 / 2 / 1 at most
         T = 150
         st = random_state(orc, B, rng, spread=0.5)
@@ -334,14 +345,15 @@ def test_time_major_envs_per_thread_and_fallbacks(excenvs, env, solver):
         base = e.vmap_sim_ahead(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major", block_envs=1)
         for v in (0, 2, 4):
             other = e.vmap_sim_ahead(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major", block_envs=v)
-            assert torch.equal(base[0], other[0]), (B, v)
-            for name in e.PHYS_FIELDS:
-                assert torch.equal(getattr(base[1].physical_state, name), getattr(other[1].physical_state, name))
-                assert torch.equal(getattr(base[2].physical_state, name), getattr(other[2].physical_state, name))
+            assert same(base[0], other[0]), (B, v)
+            for name, sc in zip(e.PHYS_FIELDS, scales):
+                assert same(getattr(base[1].physical_state, name), getattr(other[1].physical_state, name), sc)
+                assert same(getattr(base[2].physical_state, name), getattr(other[2].physical_state, name), sc)
         full = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major")
-        assert torch.equal(base[0], full[0])
+        assert same(base[0], full[0])
         bm = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau)
-        assert torch.equal(full[4], bm[4]) and torch.equal(full[5], bm[5]) and torch.equal(full[3], bm[3])
+        clear = (bm[0].abs() - 1).abs() > 1e-4  # flags away from the threshold cannot depend on the last bit
+        assert torch.equal(full[4][clear], bm[4][clear]) and torch.equal(full[5], bm[5]) and torch.equal(full[3], bm[3])
         assert full[3].shape == (B, T, 1) and full[4].shape == (B, T + 1, orc.n_trunc) and full[5].shape == (B, T, 1)
 
 
