@@ -158,7 +158,7 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-KERNELS = {"time_major": ("simtm", "exenv::simtm_kernel<MassSpringDamper<float>, Tsit5, float, W=4, V=4>"),
+KERNELS = {"time_major": ("simtm", "exenv::simtm_packed_kernel<MassSpringDamper<float>, Tsit5, W=4, V=4> (FFMA2)"),
            "batch_major": ("sim", "exenv::sim_kernel<MassSpringDamper<float>, Tsit5, float>")}
 
 
@@ -337,8 +337,8 @@ def run_b200(args):
                              "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
                              "ncu": {k: facts.get(k) for k in ("issue_slots_busy", "fma_pipe_busy", "dram_pct_of_peak",
                                                                 "warp_instructions_per_env_step", "source")},
-                             "note": "the Tsit5 trajectory kernel is bound by instruction issue (7 right-hand sides + "
-                                     "dense output per env-step), not by HBM; see profiles/README.md"},
+                             "note": "the Tsit5 trajectory kernel is bound by the fp32 FMA pipe (7 right-hand sides + dense "
+                                     "output per env-step: 127 fp32 operations), not by HBM; see profiles/README.md"},
                 "other_layout": other}
         if not args.no_cpu_baseline and world == 1:
             try:
