@@ -227,9 +227,10 @@ def test_full_size_linearity_property(excenvs, layout):
     for s in (s1, s2):
         s.PRNGKey = nan
         s.reference = e.PhysicalState(nan, nan)
-    _, st1, _ = e.vmap_sim_ahead(s1, acts, 1e-4, 1e-4, layout=layout)
+    kw = dict(layout=layout, block_envs=4) if layout == "time_major" else {}  # 4 envs / thread: the packed FFMA2 kernel
+    _, st1, _ = e.vmap_sim_ahead(s1, acts, 1e-4, 1e-4, **kw)
     # action normalisation is affine with zero offset (min = -max), so scaling the normalised action scales the force
-    _, st2, _ = e.vmap_sim_ahead(s2, 2 * acts, 1e-4, 1e-4, layout=layout)
+    _, st2, _ = e.vmap_sim_ahead(s2, 2 * acts, 1e-4, 1e-4, **kw)
     d = (st2.physical_state.deflection - 2 * st1.physical_state.deflection).abs().max().item()
     v = (st2.physical_state.velocity - 2 * st1.physical_state.velocity).abs().max().item()
     assert d < 1e-5 and v < 1e-4
@@ -349,12 +350,15 @@ def test_time_major_envs_per_thread_and_fallbacks(excenvs, env, solver):
             for name, sc in zip(e.PHYS_FIELDS, scales):
                 assert same(getattr(base[1].physical_state, name), getattr(other[1].physical_state, name), sc)
                 assert same(getattr(base[2].physical_state, name), getattr(other[2].physical_state, name), sc)
-        full = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major")
-        assert same(base[0], full[0])
         bm = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau)
         clear = (bm[0].abs() - 1).abs() > 1e-4  # flags away from the threshold cannot depend on the last bit
-        assert torch.equal(full[4][clear], bm[4][clear]) and torch.equal(full[5], bm[5]) and torch.equal(full[3], bm[3])
-        assert full[3].shape == (B, T, 1) and full[4].shape == (B, T + 1, orc.n_trunc) and full[5].shape == (B, T, 1)
+        for v in (0, 1, 2, 4):  # fused-epilogue flavour of every width (v = 0: the automatic choice)
+            full = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major",
+                                                  block_envs=v)
+            assert same(base[0], full[0]), (B, v)
+            assert torch.equal(full[4][clear], bm[4][clear]) and torch.equal(full[5], bm[5]), (B, v)
+            assert torch.equal(full[3], bm[3]), (B, v)
+            assert full[3].shape == (B, T, 1) and full[4].shape == (B, T + 1, orc.n_trunc) and full[5].shape == (B, T, 1)
 
 
 def test_time_major_c_abi_misaligned_and_partial_outputs(excenvs):
