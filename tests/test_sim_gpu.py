@@ -432,3 +432,40 @@ def test_config4_pmsm_saturated_full_horizon_properties(excenvs):
     for name in ("i_d", "i_q", "torque"):
         a, b = getattr(st_full.physical_state, name), getattr(st_bm.physical_state, name)
         assert ((a - b).abs().max() / scales[name]).item() < 1e-3, name
+
+
+@pytest.mark.parametrize("layout", ["batch_major", "time_major"])
+@pytest.mark.parametrize("env,solver", [("mass_spring_damper", O.TSIT5), ("pendulum", O.EULER), ("pmsm", O.TSIT5)])
+def test_trajectory_kernels_write_only_their_outputs(excenvs, env, solver, layout):
+    """Guard zones around every output buffer stay untouched (ragged batches, every envs-per-thread width, the first
+    step's double save, the L2 prefetch running ahead of the action stream near its end)."""
+    rng = np.random.default_rng(31)
+    orc = O.Oracle(env, solver=solver, dtype=np.float32)
+    G = 256  # guard floats on either side
+    for B, T in ((388, 37), (390, 5), (129, 1), (4 * 1024, 9)):
+        st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=(env == "pmsm"))
+        acts = torch.as_tensor(rng.uniform(-1, 1, (B, T, orc.A)).astype(np.float32), device="cuda") * 0.05
+        e = make_env(excenvs, orc, B)
+        NS, OW, D = T + 1, e.obs_dim, e.physical_state_dim
+        sizes = [NS * B * OW] + [NS * B] * D
+        buf = torch.full((sum(sizes) + G * (len(sizes) + 1),), 12345.0, device="cuda")
+        views, off = [], G
+        for n in sizes:
+            views.append(buf[off:off + n])
+            off += n + G
+        tm = layout == "time_major"
+        out = dict(obs=views[0].view((NS, B, OW) if tm else (B, NS, OW)),
+                   traj=[v.view((NS, B) if tm else (B, NS)) for v in views[1:]])
+        for v in ((0, 1, 2, 4) if tm else (0,)):
+            for x in views:
+                x.fill_(777.0)
+            e._sim_impl(e.env_properties, B, to_state(e, st), acts, orc.tau, orc.tau, out=out, layout=layout,
+                        block_envs=v)
+            torch.cuda.synchronize()
+            off = 0
+            for n in sizes:
+                assert bool((buf[off:off + G] == 12345.0).all()), (B, T, v, "guard before")
+                off += G + n
+            assert bool((buf[off:off + G] == 12345.0).all()), (B, T, v, "guard after")
+            for x in views:
+                assert not bool((x == 777.0).any()), (B, T, v, "unwritten output")
