@@ -112,6 +112,27 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """Run this rank (and first-touch its pinned host buffers) on the CPU cores next to its GPU: the host-buffer leg is
+    PCIe bound and a far-socket buffer halves it.  Best effort: only cores this process is already allowed to use."""
+    try:
+        import pynvml
+        import torch
+
+        pr = torch.cuda.get_device_properties(dev_index)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        near = {64 * i + b for i, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(near & allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+        return {"near_gpu": len(near), "allowed": len(allowed), "bound_to": len(cpus) if cpus else len(allowed)}
+    except Exception as exc:  # no NVML, no permission, ...: keep the inherited affinity
+        return {"error": str(exc)[:80]}
+
+
 # ---- clocks ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -182,6 +203,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -311,7 +333,7 @@ def run_b200(args):
             ok = bool(torch.equal(h_obs[:64], chk))
             e2e = {"value": world * B * T_STEPS * n_e2e / float(tt.item()), "unit": "env-steps/s",
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
-                   "batch_per_gpu": B, "matches_device_path": ok,
+                   "batch_per_gpu": B, "matches_device_path": ok, "cpu_affinity": affinity,
                    "how": "exenv_sim_ahead_host: pinned host buffers, chunked H2D / kernel / D2H on 3 streams, "
                           "wall clock around the blocking C call (max over ranks)"}
             del h_obs, h_traj, h_act
