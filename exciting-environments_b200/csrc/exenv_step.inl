@@ -81,7 +81,7 @@ __device__ __forceinline__ void store_bytes(uint8_t *dst, const uint8_t *v) {
 // MODE 2: generic (runtime n_control, runtime epilogue pointers, references; rows written with scalar stores)
 template <class Env, int SOLVER, typename T>
 constexpr int step_min_blocks() {
-  if (Env::IS_PMSM) return sizeof(T) == 4 ? 2 : 1;  // 7 state + 8 obs scalars per env: needs the registers
+  if (Env::IS_PMSM) return sizeof(T) == 4 ? 3 : 2;  // 7 state + 8 obs scalars per env, two (one) envs per thread
   return SOLVER == EXENV_EULER ? (sizeof(T) == 4 ? 4 : 3) : (sizeof(T) == 4 ? 3 : 2);
 }
 
@@ -105,7 +105,11 @@ __global__ void __launch_bounds__(256, step_min_blocks<Env, SOLVER, T>())
       for (int v = 0; v < VEC; ++v) s[v][d] = tmp[v];
     }
 #pragma unroll
-    for (int i = 0; i < A; ++i) vload<T, VEC>(a.action + b0 * A + i * VEC, act + i * VEC);
+    {  // VEC * A contiguous scalars with the widest (<= 16-byte) vectors
+      constexpr int VW = (VEC * A) % (16 / (int)sizeof(T)) == 0 ? 16 / (int)sizeof(T) : VEC;
+#pragma unroll
+      for (int i = 0; i < VEC * A / VW; ++i) vload<T, VW>(a.action + b0 * A + i * VW, act + i * VW);
+    }
   }
 
   T ob[VEC * O], fl[VEC][NODE];
@@ -182,9 +186,12 @@ __global__ void __launch_bounds__(256, step_min_blocks<Env, SOLVER, T>())
         vstore<T, VEC>(a.kout[d] + b0, tmp);
       }
     }
-    if constexpr (MODE != 2) {  // VEC * O contiguous scalars = O vectors
+    if constexpr (MODE != 2) {  // VEC * O contiguous scalars
+      {
+        constexpr int VW = (VEC * O) % (16 / (int)sizeof(T)) == 0 ? 16 / (int)sizeof(T) : VEC;
 #pragma unroll
-      for (int i = 0; i < O; ++i) vstore<T, VEC>(a.obs + b0 * O + i * VEC, ob + i * VEC);
+        for (int i = 0; i < VEC * O / VW; ++i) vstore<T, VW>(a.obs + b0 * O + i * VW, ob + i * VW);
+      }
     }
     if constexpr (MODE == 1) {
       if (a.reward) vstore<T, VEC>(a.reward + b0, rew);
@@ -379,7 +386,9 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 template <class Env, int SOLVER, typename T, bool PER_ENV>
 static int launch_step_t(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStream_t stream) {
-  constexpr int VEC = 16 / sizeof(T);
+  // environments per thread: 16-byte vectors; PMSM (7 leaves + 8 observation entries per environment) 8-byte ones, so
+  // that twice as many warps fit the register file and cover the gap between its load and store phases
+  constexpr int VEC = (Env::IS_PMSM ? 8 : 16) / sizeof(T);
   StepK<T> a{};
   bool vec_ok = true;
   for (int d = 0; d < Env::D; ++d) {
