@@ -386,9 +386,12 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 template <class Env, int SOLVER, typename T, bool PER_ENV>
 static int launch_step_t(const ExenvPlan &plan, const ExenvStepArgs &x, cudaStream_t stream) {
-  // environments per thread: 16-byte vectors; PMSM (7 leaves + 8 observation entries per environment) 8-byte ones, so
-  // that twice as many warps fit the register file and cover the gap between its load and store phases
-  constexpr int VEC = (Env::IS_PMSM ? 8 : 16) / sizeof(T);
+  // environments per thread: 16-byte vectors; 8-byte ones where the per-environment state is large (PMSM: 7 leaves + 8
+  // observation entries; cart-pole / acrobot Tsit5 fp32 and Euler fp64), so that twice as many warps fit the register
+  // file and cover the gap between the load and store phases (measured on B200, profiles/README.md)
+  constexpr bool NARROW = Env::IS_PMSM || (Env::ID >= 3 && ((SOLVER == EXENV_TSIT5 && sizeof(T) == 4) ||
+                                                            (SOLVER == EXENV_EULER && sizeof(T) == 8)));
+  constexpr int VEC = (NARROW ? 8 : 16) / sizeof(T);
   StepK<T> a{};
   bool vec_ok = true;
   for (int d = 0; d < Env::D; ++d) {
