@@ -132,7 +132,8 @@ struct Pendulum {
   template <bool FAST>
   EX_HD static void rhs(const T *y, const T *u, const T *, const Pre &q, const Aux &, T *dy) {
     dy[0] = y[1];
-    dy[1] = div_inv<FAST, T>(u[0] + q.lmg * Mth<T>::sin(y[0]), q.ml2);
+    if constexpr (FAST) dy[1] = div_mul<T>(u[0] + q.lmg * Mth<T>::sin(y[0]), q.ml2);
+    else dy[1] = div_inv<false, T>(u[0] + q.lmg * Mth<T>::sin(y[0]), q.ml2);
   }
   EX_HD static void post(T *y) { y[0] = wrap_pi<T>(y[0]); }  // :188, :241
   EX_HD static bool is_angle(int f) { return f == 0; }
@@ -150,10 +151,17 @@ struct MassSpringDamper {
   using Aux = NoAux;
   struct Pre {
     InvDiv<T> m;
+    T dm, km;  // d / m, k / m
+    T a1, a0;  // force / m as one FMA of the normalised action: a1 * z + a0
   };
   EX_HD static Pre precompute(const T *p) {
     Pre q;
     q.m = make_invdiv<T>(p[2]);
+    q.dm = p[0] / p[2];
+    q.km = p[1] / p[2];
+    const T amin = p[NSTATIC + 2 * D], amax = p[NSTATIC + 2 * D + 1];
+    q.a1 = (amax - amin) / ((T)2 * p[2]);
+    q.a0 = (amax + amin) / ((T)2 * p[2]);
     return q;
   }
   // :142-148  p = d, k, m
@@ -162,6 +170,16 @@ struct MassSpringDamper {
     const T d = p[0], k = p[1];
     dy[0] = y[1];
     dy[1] = div_inv<FAST, T>(u[0] - d * y[1] - k * y[0], q.m);
+  }
+  // The trajectory kernels' form of the same right-hand side (env_sim_prescaled below): the window of zero-order-hold
+  // actions holds um = force / m (act_sim: de-normalisation and the division by m folded into one FMA of the
+  // normalised action), and dv/dt = um - (d/m) v - (k/m) x is two FMAs with prepared quotients instead of two FMAs and
+  // a correctly rounded division.  The acceleration differs from the expression above by a few ulp (the north star's
+  // per-step tolerance is 1e-6 relative; tests/test_sim_gpu.py and tests/test_hostcheck.py hold it against the oracle).
+  EX_HD static T act_sim(T z, const Pre &q) { return fma_(q.a1, z, q.a0); }
+  EX_HD static void rhs_sim(const T *y, const T *um, const Pre &q, T *dy) {
+    dy[0] = y[1];
+    dy[1] = fma_(-q.dm, y[1], fma_(-q.km, y[0], um[0]));
   }
   EX_HD static void post(T *) {}
   EX_HD static bool is_angle(int) { return false; }
@@ -178,6 +196,17 @@ struct env_packable {
 };
 template <>
 struct env_packable<MassSpringDamper<float>> {
+  static constexpr bool value = true;
+};
+
+// Environments whose trajectory kernels keep pre-scaled actions in the zero-order-hold window and evaluate
+// Env::rhs_sim(y, u_prescaled, pre, dy) instead of Env::rhs<true> (sim_rhs / prepare_action in exenv_sim_core.cuh).
+template <class Env>
+struct env_sim_prescaled {
+  static constexpr bool value = false;
+};
+template <typename T>
+struct env_sim_prescaled<MassSpringDamper<T>> {
   static constexpr bool value = true;
 };
 
@@ -203,7 +232,8 @@ struct FluidTank {
   template <bool FAST>
   EX_HD static void rhs(const T *y, const T *u, const T *, const Pre &q, const Aux &, T *dy) {
     const T h = y[0] < (T)0 ? (T)0 : y[0];
-    dy[0] = div_inv<FAST, T>(u[0], q.Ab) - q.coef * Mth<T>::sqrt(q.two_g * h);
+    if constexpr (FAST) dy[0] = div_mul<T>(u[0], q.Ab) - q.coef * Mth<T>::sqrt(q.two_g * h);
+    else dy[0] = div_inv<false, T>(u[0], q.Ab) - q.coef * Mth<T>::sqrt(q.two_g * h);
   }
   EX_HD static void post(T *y) { y[0] = y[0] < (T)0 ? (T)0 : y[0]; }  // :146, :196
   EX_HD static bool is_angle(int) { return false; }
@@ -233,10 +263,18 @@ struct CartPole {
     T s, c;
     Mth<T>::sincos(th, &s, &c);
     const T sg = sign_of<T>(v);
-    const T d_om = (g * s + c * div_inv<FAST, T>(-u[0] - q.mpl.d * (om * om) * s + mu_c * sg, q.M) -
-                    div_inv<FAST, T>(mu_p * om, q.mpl)) /
-                   (l * ((T)(4.0 / 3.0) - div_inv<FAST, T>(m_p * (c * c), q.M)));
-    const T d_v = div_inv<FAST, T>(u[0] + q.mpl.d * ((om * om) * s - d_om * c) - mu_c * sg, q.M);
+    T d_om, d_v;
+    if constexpr (FAST) {  // quotients by parameters as products with the prepared reciprocal, the one state-dependent
+                           // division as a Newton-refined reciprocal (exenv_math.cuh: div_mul, rcp_nr)
+      d_om = (g * s + c * div_mul<T>(-u[0] - q.mpl.d * (om * om) * s + mu_c * sg, q.M) - div_mul<T>(mu_p * om, q.mpl)) *
+             rcp_nr(l * ((T)(4.0 / 3.0) - div_mul<T>(m_p * (c * c), q.M)));
+      d_v = div_mul<T>(u[0] + q.mpl.d * ((om * om) * s - d_om * c) - mu_c * sg, q.M);
+    } else {
+      d_om = (g * s + c * div_inv<false, T>(-u[0] - q.mpl.d * (om * om) * s + mu_c * sg, q.M) -
+              div_inv<false, T>(mu_p * om, q.mpl)) /
+             (l * ((T)(4.0 / 3.0) - div_inv<false, T>(m_p * (c * c), q.M)));
+      d_v = div_inv<false, T>(u[0] + q.mpl.d * ((om * om) * s - d_om * c) - mu_c * sg, q.M);
+    }
     dy[0] = v;
     dy[1] = d_v;
     dy[2] = om;
@@ -270,12 +308,29 @@ struct Acrobot {
     const T d22 = m2 * (lc2 * lc2) + I2;
     const T h1 = -m2 * l1 * lc2 * s2 * (om2 * om2) - (T)2 * m2 * l1 * lc2 * s2 * om1 * om2;
     const T h2 = m2 * l1 * lc2 * s2 * (om1 * om1);
-    const T ca = Mth<T>::cos(th1 + Cst<T>::half_pi());
-    const T cb = Mth<T>::cos(th1 + th2 + Cst<T>::half_pi());
+    T ca, cb, d_om1, d_om2;
+    if constexpr (FAST) {  // cos(x + pi/2) = -sin(x): one sincos of theta_1 and the angle-sum identity replace two
+                           // cosines (the reference's arguments carry the rounding of x + fl(pi/2), i.e. a few 1e-7 of
+                           // noise in fp32; the values agree to that level)
+      T s1, c1;
+      Mth<T>::sincos(th1, &s1, &c1);
+      ca = -s1;
+      cb = -(s1 * c2 + c1 * s2);
+    } else {
+      ca = Mth<T>::cos(th1 + Cst<T>::half_pi());
+      cb = Mth<T>::cos(th1 + th2 + Cst<T>::half_pi());
+    }
     const T phi1 = (m1 * lc1 + m2 * l1) * g * ca + m2 * lc2 * g * cb;
     const T phi2 = m2 * lc2 * g * cb;
-    const T d_om1 = (T)1 / (d12 - d22 / d12 * d11) * (u[0] + d22 / d12 * (h1 + phi1) - h2 - phi2);
-    const T d_om2 = (-d11 * d_om1 - h1 - phi1) / d12;
+    if constexpr (FAST) {  // three divisions by two state-dependent denominators -> two Newton-refined reciprocals
+      const T r12 = rcp_nr(d12);
+      const T qq = d22 * r12;
+      d_om1 = rcp_nr(d12 - qq * d11) * (u[0] + qq * (h1 + phi1) - h2 - phi2);
+      d_om2 = (-d11 * d_om1 - h1 - phi1) * r12;
+    } else {
+      d_om1 = (T)1 / (d12 - d22 / d12 * d11) * (u[0] + d22 / d12 * (h1 + phi1) - h2 - phi2);
+      d_om2 = (-d11 * d_om1 - h1 - phi1) / d12;
+    }
     dy[0] = om1;
     dy[1] = om2;
     dy[2] = d_om1;

@@ -97,9 +97,59 @@ EX_HD T div_inv(T x, const InvDiv<T> &c) {
     return x / c.d;
   }
 }
+// x / d as x * RN(1 / d): one rounding more than div_inv (<= 1.5 ulp from the quotient).  The FAST right-hand sides of
+// the instruction-bound environments use it where the quotient only feeds a derivative.
+template <typename T>
+EX_HD T div_mul(T x, const InvDiv<T> &c) {
+  return x * c.r;
+}
+// 1 / d for a state-dependent denominator without the IEEE division's range checks and slow path: the hardware
+// approximation refined by Newton steps (float: one, about 1 ulp; double: two from the 2^-23 seed).  The caller
+// guarantees a normal, non-zero d (physical inertia terms); inf / nan propagate.
+EX_HD float rcp_nr(float d) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return ::fmaf(r, ::fmaf(-d, r, 1.0f), r);
+#else
+  return 1.0f / d;
+#endif
+}
+EX_HD double rcp_nr(double d) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = ::fma(r, ::fma(-d, r, 1.0), r);
+  return ::fma(r, ::fma(-d, r, 1.0), r);
+#else
+  return 1.0 / d;
+#endif
+}
 template <bool FAST, typename T>
 EX_HD T norm_inv(T x, T mn, const InvDiv<T> &span) {
   return div_inv<FAST, T>((T)2 * (x - mn), span) - (T)1;
+}
+
+// The same normalisation as ONE fused multiply-add, 2 (x - mn) / (mx - mn) - 1 = c1 x + c0 with c1 = 2 / (mx - mn) and
+// c0 = -2 mn / (mx - mn) - 1 prepared by true divisions (c0 is exactly 0 for the symmetric ranges, exactly -1 for
+// ranges starting at 0).  One rounding of the exact c1 x + c0 instead of three roundings: within 1.5 ulp of 1 of the
+// reference's value (observations live in [-1, 1]; the north star's tolerance is 1e-6).  Used by the time-major
+// trajectory kernels, where the correctly rounded form costs six instructions per observation entry; the truncation
+// flags those kernels emit are computed from the very observation values they return.
+template <typename T>
+struct NormFma {
+  T c1, c0;
+};
+template <typename T>
+EX_HD NormFma<T> make_normfma(T mn, T mx) {
+  NormFma<T> n;
+  n.c1 = (T)2 / (mx - mn);
+  n.c0 = -(((T)2 * mn) / (mx - mn)) - (T)1;
+  return n;
+}
+template <typename T>
+EX_HD T norm_fma(T x, const NormFma<T> &n) {
+  return fma_(x, n.c1, n.c0);
 }
 
 // C fmod(x, y) for y > 0, exactly, without libm's iterative reduction when the quotient is moderate (angles: a few

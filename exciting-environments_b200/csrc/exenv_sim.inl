@@ -519,8 +519,8 @@ __global__ void __launch_bounds__(SIM_E)
         T raw[A], u[A];
 #pragma unroll
         for (int c = 0; c < A; ++c) raw[c] = col[(k * A + c) * SIM_EP];
-        prepare_action<Env, T>((long)ti.act_lo + k, raw, s0, p, a.deadtime, a.n_actions, a.pmsm_adv, a.pmsm_lin_stop,
-                               u);
+        prepare_action<Env, T>((long)ti.act_lo + k, raw, s0, p, pre, a.deadtime, a.n_actions, a.pmsm_adv,
+                               a.pmsm_lin_stop, u);
 #pragma unroll
         for (int c = 0; c < A; ++c) col[(k * A + c) * SIM_EP] = u[c];
       }
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(SIM_E)
 #pragma unroll
         for (int i = 0; i < NODE; ++i) yl[i] = last[i];
       }
-      Env::template rhs<true>(yl, u, p, pre, aux, fi);
+      sim_rhs<Env, T>(yl, u, p, pre, aux, fi);
 #pragma unroll
       for (int i = 0; i < NODE; ++i) a.klast[i][b] = fi[i];
     }

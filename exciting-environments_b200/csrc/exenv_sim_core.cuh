@@ -56,12 +56,17 @@ EX_HD void fetch_stage_(F &f, uint64_t w, int s, T *u, long) {
 //  generic envs : denormalize_action of raw action q                               (core_env.py:468)
 //  PMSM         : q < deadtime -> the initial u_dq buffer; else raw action j = q - deadtime clipped to the voltage
 //                 hexagon at eps_j = eps_0 + linspace(0, tau*(L-1), L)[j] * omega_el   (pmsm_env.py:709-777)
+//  pre-scaled  : environments marked env_sim_prescaled keep Env::act_sim(raw, pre) instead (the de-normalised action
+//                 already divided by the parameter the right-hand side divides it by), consumed by Env::rhs_sim
 // `raw` = normalised raw action (A values; ignored for buffer entries), s0 = initial physical state.
 template <class Env, typename T>
-EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, int deadtime, long n_actions, T pmsm_adv,
-                          T pmsm_lin_stop, T *u) {
+EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, const typename Env::Pre &pre, int deadtime,
+                          long n_actions, T pmsm_adv, T pmsm_lin_stop, T *u) {
   const T *an = p + Env::NSTATIC + 2 * Env::D;
-  if constexpr (Env::IS_PMSM) {
+  if constexpr (env_sim_prescaled<Env>::value) {
+#pragma unroll
+    for (int c = 0; c < Env::A; ++c) u[c] = Env::act_sim(raw[c], pre);
+  } else if constexpr (Env::IS_PMSM) {
     if (q < deadtime) {
       u[0] = s0[0];
       u[1] = s0[1];
@@ -78,6 +83,13 @@ EX_HD void prepare_action(long q, const T *raw, const T *s0, const T *p, int dea
 #pragma unroll
     for (int c = 0; c < Env::A; ++c) u[c] = denorm_mm<T>(raw[c], an[2 * c], an[2 * c + 1]);
   }
+}
+
+// Right-hand side as the trajectory kernels evaluate it: `u` is what prepare_action stored.
+template <class Env, typename T>
+EX_HD void sim_rhs(const T *y, const T *u, const T *p, const typename Env::Pre &pre, typename Env::Aux &aux, T *dy) {
+  if constexpr (env_sim_prescaled<Env>::value) Env::rhs_sim(y, u, pre, dy);
+  else Env::template rhs<true>(y, u, p, pre, aux, dy);
 }
 
 // One solver step + its saves.
@@ -138,7 +150,7 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
   if constexpr (SOLVER == EXENV_EULER) {  // diffrax.Euler
     T u[A], f0[NODE];
     fetch_stage_(fetch, w, 0, u, 0);
-    Env::template rhs<true>(y, u, p, pre, aux, f0);
+    sim_rhs<Env, T>(y, u, p, pre, aux, f0);
 #pragma unroll
     for (int i = 0; i < NODE; ++i) {
       k[0][i] = f0[i] * dt;
@@ -151,7 +163,7 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
         [&](int stage, const T *ys, T *fo) {
           T u[A];
           fetch_stage_(fetch, w, stage, u, 0);
-          Env::template rhs<true>(ys, u, p, pre, aux, fo);
+          sim_rhs<Env, T>(ys, u, p, pre, aux, fo);
         },
         y1, fl, k);
 #pragma unroll
@@ -182,7 +194,7 @@ EX_HD void sim_first_derivative(uint64_t w0, const T *y, T *f, const T *p, const
                                 typename Env::Aux &aux, Fetch &&fetch) {
   T u[Env::A];
   fetch_stage_(fetch, w0, 0, u, 0);
-  Env::template rhs<true>(y, u, p, pre, aux, f);
+  sim_rhs<Env, T>(y, u, p, pre, aux, f);
 }
 
 }  // namespace exenv

@@ -31,7 +31,18 @@
 
 namespace exenv {
 
-constexpr int SIMTM_THREADS = 128;
+constexpr int SIMTM_THREADS = 128;  // largest CTA (launch bounds)
+// Threads per CTA actually launched.  A trajectory kernel's work item is a whole trajectory, so the grid runs as a few
+// long "waves" of resident CTAs and the last, partially filled one decides the tail; smaller CTAs spread that tail
+// over the SMs more evenly.  EXENV_SIMTM_THREADS (32, 64, 96 or 128) overrides the default for A/B measurements.
+static int simtm_block_threads() {
+  static const int n = [] {
+    const char *e = getenv("EXENV_SIMTM_THREADS");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 32 && v <= SIMTM_THREADS && v % 32 == 0) ? v : SIMTM_THREADS;
+  }();
+  return n;
+}
 
 template <typename T>
 struct SimTmK {
@@ -323,13 +334,14 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     for (int i = 0; i < NST; ++i) last[v][i] = (T)0;
   }
 
-  // observation normalisation: prepared reciprocal of every span (correctly rounded quotient, exenv_math.cuh)
-  InvDiv<T> sdiv[D];
+  // observation normalisation: one FMA per entry with prepared coefficients (norm_fma, exenv_math.cuh); every
+  // instantiation of this kernel (vector, fused-epilogue, generic) and the packed kernel use the same form
+  NormFma<T> nf[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<T>(pn[2 * d + 1] - pn[2 * d]);
+  for (int d = 0; d < D; ++d) nf[d] = make_normfma<T>(pn[2 * d], pn[2 * d + 1]);
   T om_norm[V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) om_norm[v] = Env::IS_PMSM ? norm_inv<true, T>(s0[v][D - 1], pn[2 * (D - 1)], sdiv[D - 1]) : (T)0;
+  for (int v = 0; v < V; ++v) om_norm[v] = Env::IS_PMSM ? norm_fma<T>(s0[v][D - 1], nf[D - 1]) : (T)0;
   T rf[D];
   if constexpr (GENERIC) {
 #pragma unroll
@@ -373,7 +385,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     q = q < q_max ? q : q_max;
 #pragma unroll
     for (int v = 0; v < V; ++v)
-      prepare_action<Env, T>((long)q, raw[v], s0[v], p, a.deadtime, a.n_actions, a.pmsm_adv, a.pmsm_lin_stop,
+      prepare_action<Env, T>((long)q, raw[v], s0[v], p, pre, a.deadtime, a.n_actions, a.pmsm_adv, a.pmsm_lin_stop,
                              win[v].uw[k]);
   };
 #pragma unroll
@@ -430,17 +442,17 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   long step_first_save = 0;  // save index the running pointers address
   auto obs_fast = [&](int v, const T *st, const T *sv, T *ob) {
     if constexpr (Env::IS_PMSM) {
-      ob[0] = norm_inv<true, T>(sv[3], pn[6], sdiv[3]);
-      ob[1] = norm_inv<true, T>(sv[4], pn[8], sdiv[4]);
+      ob[0] = norm_fma<T>(sv[3], nf[3]);
+      ob[1] = norm_fma<T>(sv[4], nf[4]);
       ob[2] = om_norm[v];
-      ob[3] = norm_inv<true, T>(sv[5], pn[10], sdiv[5]);
+      ob[3] = norm_fma<T>(sv[5], nf[5]);
       ob[4] = st[6];
       ob[5] = st[7];
-      ob[6] = norm_inv<true, T>(sv[0], pn[0], sdiv[0]);
-      ob[7] = norm_inv<true, T>(sv[1], pn[2], sdiv[1]);
+      ob[6] = norm_fma<T>(sv[0], nf[0]);
+      ob[7] = norm_fma<T>(sv[1], nf[1]);
     } else {
 #pragma unroll
-      for (int o = 0; o < O; ++o) ob[o] = norm_inv<true, T>(sv[o], pn[2 * o], sdiv[o]);
+      for (int o = 0; o < O; ++o) ob[o] = norm_fma<T>(sv[o], nf[o]);
     }
   };
   auto sink_v = [&](int v, long sidx, const T *st) {
@@ -478,7 +490,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
       for (int d = 0; d < D; ++d)
         if (a.traj[d]) __stcs(a.traj[d] + row, sv[d]);
       T ob[O + EXENV_MAX_CONTROL];
-      observe<Env, T>(sv, p, ob);
+      obs_fast(0, st, sv, ob);
 #pragma unroll
       for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
         if (j < a.n_control) ob[O + j] = norm_field<Env, T>(a.control[j], rf, p);
@@ -613,7 +625,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
 #pragma unroll
         for (int i = 0; i < NODE; ++i) yl[i] = last[v][i];
       }
-      Env::template rhs<true>(yl, u, p, pre, aux[v], fi[v]);
+      sim_rhs<Env, T>(yl, u, p, pre, aux[v], fi[v]);
     }
   }
 #pragma unroll
@@ -682,8 +694,9 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
     }
   }
   const long threads = (x.batch + V - 1) / V;
-  const unsigned grid = (unsigned)((threads + SIMTM_THREADS - 1) / SIMTM_THREADS);
-  kern<<<grid, SIMTM_THREADS, smem, stream>>>(a, kp);
+  const int nthr = simtm_block_threads();
+  const unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
+  kern<<<grid, nthr, smem, stream>>>(a, kp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -51,9 +51,9 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
 #pragma unroll
     for (int i = 0; i < NST; ++i) last[vv][i] = P(0.0f);
   }
-  InvDiv<P> sdiv[D];
+  NormFma<P> nf[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<P>(pn[2 * d + 1] - pn[2 * d]);
+  for (int d = 0; d < D; ++d) nf[d] = make_normfma<P>(pn[2 * d], pn[2 * d + 1]);
 
   // ---- window of prepared ZOH actions (see exenv_simtm.inl) ------------------------------------------------------
   const int q_max = (int)a.n_actions - 1;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
       P rp[A];
 #pragma unroll
       for (int c = 0; c < A; ++c) rp[c] = P(raw[2 * vv][c], raw[2 * vv + 1][c]);
-      prepare_action<EnvP, P>((long)q, rp, s0[vv], pq, 0, a.n_actions, P(0.0f), P(0.0f), win[vv].uw[k]);
+      prepare_action<EnvP, P>((long)q, rp, s0[vv], pq, pre, 0, a.n_actions, P(0.0f), P(0.0f), win[vv].uw[k]);
     }
   };
 #pragma unroll
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   long step_first_save = 0;
   auto observe_pair = [&](const P *sv, P *ob) {
 #pragma unroll
-    for (int o = 0; o < O; ++o) ob[o] = norm_inv<true, P>(sv[o], pn[2 * o], sdiv[o]);
+    for (int o = 0; o < O; ++o) ob[o] = norm_fma<P>(sv[o], nf[o]);
   };
   auto flags_lane = [&](const T *sv, const T *ob, uint8_t *tr, uint8_t &te) {  // control_state == []
     bool t0 = false;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
       win[vv](q_last, u);
 #pragma unroll
       for (int i = 0; i < NODE; ++i) yl[i] = last[vv][i];
-      EnvP::template rhs<true>(yl, u, pq, pre, aux, fp);
+      sim_rhs<EnvP, P>(yl, u, pq, pre, aux, fp);
 #pragma unroll
       for (int i = 0; i < NODE; ++i) {
         fi[2 * vv][i] = fp[i].x;
@@ -312,8 +312,9 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
 template <class Env, int SOLVER, int W, int V, bool EPI>
 static int launch_simtm_packed_v(const SimTmK<float> &a, const KParams<float> &kp, long batch, cudaStream_t stream) {
   const long threads = (batch + V - 1) / V;
-  const unsigned grid = (unsigned)((threads + SIMTM_THREADS - 1) / SIMTM_THREADS);
-  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, SIMTM_THREADS, 0, stream>>>(a, kp);
+  const int nthr = simtm_block_threads();
+  const unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
+  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, nthr, 0, stream>>>(a, kp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -98,7 +98,7 @@ static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, 
     auto fetch = [&](int idx, T *u) {
       const long raw = (long)idx - dead;
       const T *src = actions + (b * n_actions + (raw < 0 ? 0 : raw)) * A;
-      prepare_action<Env, T>(idx, src, s0, p, dead, n_actions, adv, lin_stop, u);
+      prepare_action<Env, T>(idx, src, s0, p, pre, dead, n_actions, adv, lin_stop, u);
     };
     if (SOLVER == EXENV_TSIT5) sim_first_derivative<Env, T>(words[0], y, f, p, pre, aux, fetch);
     for (long n = 0; n < n_steps; ++n) {
