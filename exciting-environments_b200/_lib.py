@@ -12,7 +12,8 @@ import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libexenv_b200.so"
+# EXENV_B200_LIB: load another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = Path(os.environ.get("EXENV_B200_LIB") or (_PKG / "lib" / "libexenv_b200.so"))
 HEADER_PATH = _PKG.parent / "include" / "exenv_b200.h"
 
 MAX_PARAMS, MAX_CONTROL, MAX_PHYS, MAX_ODE = 32, 8, 8, 4

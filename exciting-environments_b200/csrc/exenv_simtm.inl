@@ -18,6 +18,7 @@
 // the same host-built schedule the batch-major kernel uses (exenv_api.cu: build_schedule_t), read through L1 one
 // step ahead; the per-environment arithmetic is the same exenv_sim_core.cuh code, so both layouts produce identical
 // values.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,10 +32,12 @@
 
 namespace exenv {
 
-constexpr int SIMTM_THREADS = 128;  // largest CTA (launch bounds)
-// Threads per CTA actually launched.  A trajectory kernel's work item is a whole trajectory, so the grid runs as a few
-// long "waves" of resident CTAs and the last, partially filled one decides the tail; smaller CTAs spread that tail
-// over the SMs more evenly.  EXENV_SIMTM_THREADS (32, 64, 96 or 128) overrides the default for A/B measurements.
+constexpr int SIMTM_THREADS = 128;  // threads per CTA (launch bounds)
+// EXENV_SIMTM_THREADS (32, 64 or 96) launches smaller CTAs for A/B measurements.  Measured on the B200 (profiles/
+// README.md): a trajectory kernel's grid runs as a few long rounds of resident CTAs (2^20 environments, four per
+// thread, 512 resident threads per SM: 3.46 rounds), but the partially filled last round costs nothing -- SMs with
+// fewer resident warps finish their CTAs proportionally faster (a batch of exactly three rounds is not faster per
+// environment), and CTA sizes that make the round count integral (224 x 2) lose 12 % to register allocation.
 static int simtm_block_threads() {
   static const int n = [] {
     const char *e = getenv("EXENV_SIMTM_THREADS");
@@ -148,18 +151,27 @@ __device__ __forceinline__ void load_vec(T *v, const T *src) {
 template <typename T>
 __device__ __forceinline__ StepRec<T> load_steprec(const StepRec<T> *p) {
   StepRec<T> r;
-  uint4 q;
-  ld_chunk<16, true>(&q, p);
-  r.w = (uint64_t)q.x | ((uint64_t)q.y << 32);
-  if constexpr (sizeof(T) == 4) {
-    r.dt = __uint_as_float(q.z);
-    consume_now(q.z);
+  if constexpr (sizeof(T) == 4) {  // 8 + 4 bytes: no destination register without a consumer (a 16-byte load's padding
+                                   // lane is reused at once and its write-after-write wait queues behind the action
+                                   // load: Euler trajectories +6 %, profiles/README.md)
+    uint2 q2;
+    unsigned d;
+    ld_chunk<8, true>(&q2, p);
+    ld_chunk<4, true>(&d, reinterpret_cast<const char *>(p) + 8);
+    r.w = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
+    r.dt = __uint_as_float(d);
+    consume_now(d);
+    r.pad = (T)0;
+    return r;
   } else {
+    uint4 q;
+    ld_chunk<16, true>(&q, p);
+    r.w = (uint64_t)q.x | ((uint64_t)q.y << 32);
     r.dt = __hiloint2double((int)q.w, (int)q.z);
     consume_now(q.w);
+    r.pad = (T)0;
+    return r;
   }
-  r.pad = (T)0;
-  return r;
 }
 template <int SOLVER, typename T>
 __device__ __forceinline__ void load_saverec(SaveRec<T> &r, const SaveRec<T> *p) {
@@ -342,6 +354,18 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   T om_norm[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) om_norm[v] = Env::IS_PMSM ? norm_fma<T>(s0[v][D - 1], nf[D - 1]) : (T)0;
+  // The truncation flags (EPI / GENERIC instantiations only) are bit-exact statements about the REFERENCE's observation,
+  // abs(2 (x - min) / (max - min) - 1) > 1, so they are evaluated on the correctly rounded quotient (div_inv), not on
+  // the one-FMA value that is returned: a state exactly on the edge of its range must not be flagged.
+  InvDiv<T> sdiv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<T>(pn[2 * d + 1] - pn[2 * d]);
+  auto obs_for_flags = [&](const T *sv, T *obx) {
+    if constexpr (!Env::IS_PMSM) {  // PMSM's flag is computed from the state (trunc_entry)
+#pragma unroll
+      for (int o = 0; o < O; ++o) obx[o] = norm_inv<true, T>(sv[o], pn[2 * o], sdiv[o]);
+    }
+  };
   T rf[D];
   if constexpr (GENERIC) {
 #pragma unroll
@@ -428,11 +452,13 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   T *rwp = EPI ? a.reward + b : nullptr;  // rows of states[1:]: they start moving after save 0
   uint8_t *trp = EPI ? a.trunc + b * NT0 : nullptr;
   uint8_t *tmp = EPI ? a.term + b : nullptr;
-  auto flags_fast = [&](const T *sv, const T *ob, uint8_t *tr, uint8_t &te) {  // control_state == []
+  auto flags_fast = [&](const T *sv, const T *, uint8_t *tr, uint8_t &te) {  // control_state == []
     bool t0 = false;
+    T obx[O];
+    obs_for_flags(sv, obx);
 #pragma unroll
     for (int i = 0; i < NT0; ++i) {
-      const bool tv = trunc_entry<Env, T>(i, sv, ob, p);
+      const bool tv = trunc_entry<Env, T>(i, sv, obx, p);
       if (i == 0) t0 = tv;
       tr[i] = tv;
     }
@@ -500,10 +526,14 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
         if (o < OW) __stcs(dst + o, ob[o]);
       if (a.reward || a.trunc || a.term) {
         bool t0 = false;
+        T obx[O + EXENV_MAX_CONTROL];
+#pragma unroll
+        for (int o = O; o < O + EXENV_MAX_CONTROL; ++o) obx[o] = ob[o];  // reference entries: exact already
+        obs_for_flags(sv, obx);
 #pragma unroll
         for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
           if (i < nt) {
-            const bool tv = trunc_entry<Env, T>(i, sv, ob, p);
+            const bool tv = trunc_entry<Env, T>(i, sv, obx, p);
             if (i == 0) t0 = tv;
             if (a.trunc) a.trunc[row * nt + i] = tv;
           }
@@ -748,7 +778,7 @@ constexpr int simtm_auto_v() {
   if (Env::IS_PMSM) return 1;
   switch (Env::ID) {
     case 0: return tsit ? (f32 ? 2 : 1) : (f32 ? 4 : 1);  // pendulum
-    case 1: return tsit ? (f32 ? 4 : 2) : (f32 ? 2 : 1);  // mass-spring-damper
+    case 1: return tsit ? (f32 ? 4 : 1) : (f32 ? 2 : 1);  // mass-spring-damper
     case 2: return tsit ? (f32 ? 4 : 1) : (f32 ? 4 : 2);  // fluid tank
     case 3: return tsit ? 1 : 2;                          // cart-pole
     default: return tsit ? 1 : (f32 ? 2 : 1);             // acrobot

@@ -121,11 +121,18 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
 #pragma unroll
     for (int o = 0; o < O; ++o) ob[o] = norm_fma<P>(sv[o], nf[o]);
   };
-  auto flags_lane = [&](const T *sv, const T *ob, uint8_t *tr, uint8_t &te) {  // control_state == []
+  // flags: from the correctly rounded reference-form observation (see exenv_simtm.inl), per lane
+  InvDiv<T> sdiv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<T>(p[Env::NSTATIC + 2 * d + 1] - p[Env::NSTATIC + 2 * d]);
+  auto flags_lane = [&](const T *sv, const T *, uint8_t *tr, uint8_t &te) {  // control_state == []
     bool t0 = false;
+    T obx[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) obx[o] = norm_inv<true, T>(sv[o], p[Env::NSTATIC + 2 * o], sdiv[o]);
 #pragma unroll
     for (int i = 0; i < NT0; ++i) {
-      const bool tv = trunc_entry<Env, T>(i, sv, ob, p);
+      const bool tv = trunc_entry<Env, T>(i, sv, obx, p);
       if (i == 0) t0 = tv;
       tr[i] = tv;
     }
