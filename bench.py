@@ -166,6 +166,9 @@ class ClockSampler:
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             out["reasons"] = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in rows)]
             out["samples"] = len(sm)
+            out["sm_mhz_min"] = sm[0]
+            pw = [float(r[2]) for r in rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+            out["power_w_max"] = max(pw) if pw else None
         return out
 
 
@@ -359,8 +362,9 @@ def run_b200(args):
                              "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
                              "ncu": {k: facts.get(k) for k in ("issue_slots_busy", "fma_pipe_busy", "dram_pct_of_peak",
                                                                 "warp_instructions_per_env_step", "source")},
-                             "note": "the Tsit5 trajectory kernel is bound by the fp32 FMA pipe (7 right-hand sides + dense "
-                                     "output per env-step: 127 fp32 operations), not by HBM; see profiles/README.md"},
+                             "note": "the Tsit5 trajectory kernel sits between the fp32 FMA pipe (7 right-hand sides + dense "
+                                     "output per env-step: 97 fp32 operations as 48.5 packed instructions, pipe 62 % busy) "
+                                     "and HBM (55 % of peak under ncu); see profiles/README.md"},
                 "other_layout": other}
         if not args.no_cpu_baseline and world == 1:
             try:

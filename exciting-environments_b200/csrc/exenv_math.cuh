@@ -132,8 +132,8 @@ EX_HD T norm_inv(T x, T mn, const InvDiv<T> &span) {
 
 // The same normalisation as ONE fused multiply-add, 2 (x - mn) / (mx - mn) - 1 = c1 x + c0 with c1 = 2 / (mx - mn) and
 // c0 = -2 mn / (mx - mn) - 1 prepared by true divisions (c0 is exactly 0 for the symmetric ranges, exactly -1 for
-// ranges starting at 0).  One rounding of the exact c1 x + c0 instead of three roundings: within 1.5 ulp of 1 of the
-// reference's value (observations live in [-1, 1]; the north star's tolerance is 1e-6).  Used by the time-major
+// ranges starting at 0).  One rounding of the exact c1 x + c0 instead of three roundings: within 3 ulp of 1 (3.6e-7
+// in fp32) of the reference's value (observations live in [-1, 1]; the north star's tolerance is 1e-6).  Used by the time-major
 // trajectory kernels, where the correctly rounded form costs six instructions per observation entry; the truncation
 // flags those kernels emit are computed from the very observation values they return.
 template <typename T>
