@@ -212,9 +212,20 @@ def run_b200(args):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # its banner goes to stdout, next to the JSON line
+        # NCCL prints its version banner to stdout (NCCL_DEBUG=VERSION from the environment or from /etc/nccl.conf); stdout
+        # carries exactly one JSON line, so the communicator is created with fd 1 pointing at stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     B = args.batch
     env = ex.MassSpringDamper(batch_size=B, solver=ex.Tsit5(), tau=TAU, dtype=torch.float32, device=dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + 1000 * 2 + rank)

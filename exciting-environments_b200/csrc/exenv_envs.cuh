@@ -176,6 +176,18 @@ struct MassSpringDamper {
   // normalised action), and dv/dt = um - (d/m) v - (k/m) x is two FMAs with prepared quotients instead of two FMAs and
   // a correctly rounded division.  The acceleration differs from the expression above by a few ulp (the north star's
   // per-step tolerance is 1e-6 relative; tests/test_sim_gpu.py and tests/test_hostcheck.py hold it against the oracle).
+  // the same constants for another value type (scalar -> packed: splats that stay broadcast operands)
+  template <class SrcPre>
+  EX_HD static Pre from_scalar(const SrcPre &s) {
+    Pre q;
+    q.m.d = T(s.m.d);
+    q.m.r = T(s.m.r);
+    q.dm = T(s.dm);
+    q.km = T(s.km);
+    q.a1 = T(s.a1);
+    q.a0 = T(s.a0);
+    return q;
+  }
   EX_HD static T act_sim(T z, const Pre &q) { return fma_(q.a1, z, q.a0); }
   EX_HD static void rhs_sim(const T *y, const T *um, const Pre &q, T *dy) {
     dy[0] = y[1];

@@ -267,9 +267,35 @@ __device__ __forceinline__ void staged_to_fields(const T *st, T omega_el, T *sv)
 // GENERIC (V == 1 only): reference entries in the observation (control_state != []), the fused reward / truncated /
 // terminated outputs (vmap_generate_rew_trunc_term_ahead, core_env.py:618-647), per-environment parameters, skipped
 // (NULL) trajectory leaves.
+// Constants derived from SHARED parameters (Env::precompute, the observation normalisation) are prepared on the host
+// with the same IEEE expressions and travel in the kernel-argument constant bank: operands instead of registers (the
+// fp64 mass-spring-damper keeps two environments per thread inside 128 registers that way).  Per-environment
+// parameters are still prepared per thread.
+// Measured per environment (profiles/README.md): PMSM 123 -> 96 registers (+13 %), acrobot fp64 +19 %, fp64
+// mass-spring-damper +7 %; pendulum and fluid tank lose 7-9 % (their allocation was already minimal and the constant-bank
+// operands lengthen the dependent chains), so they keep the per-thread preparation.
+template <class Env>
+constexpr bool simtm_use_host_pre() {
+  return Env::ID == 1 || Env::ID == 4 || Env::ID == 5;
+}
+template <class Env, typename T>
+struct SimTmHostPre {
+  typename Env::Pre pre;
+  NormFma<T> nf[Env::D];
+};
+template <class Env, typename T>
+static SimTmHostPre<Env, T> make_host_pre(const KParams<T> &kp) {
+  SimTmHostPre<Env, T> h;
+  h.pre = Env::precompute(kp.v);
+  const T *pn = kp.v + Env::NSTATIC;
+  for (int d = 0; d < Env::D; ++d) h.nf[d] = make_normfma<T>(pn[2 * d], pn[2 * d + 1]);
+  return h;
+}
+
 template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
 __global__ void __launch_bounds__(SIMTM_THREADS)
-    simtm_kernel(const __grid_constant__ SimTmK<T> a, const __grid_constant__ KParams<T> kp) {
+    simtm_kernel(const __grid_constant__ SimTmK<T> a, const __grid_constant__ KParams<T> kp,
+                 const __grid_constant__ SimTmHostPre<Env, T> hp) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
   constexpr int NST = staged_values<Env>();
   static_assert(!GENERIC || V == 1, "the generic instantiation handles one environment per thread");
@@ -317,7 +343,10 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     load_env_params<Env, T, true>(kp, b, pl);
     p = pl;
   }
-  const typename Env::Pre pre = Env::precompute(p);
+  constexpr bool HOST_PRE = !PER_ENV && simtm_use_host_pre<Env>();
+  typename Env::Pre pre_thread;
+  if constexpr (!HOST_PRE) pre_thread = Env::precompute(p);
+  const typename Env::Pre &pre = HOST_PRE ? hp.pre : pre_thread;
   const T *pn = p + Env::NSTATIC;
   T s0[V][D];
 #pragma unroll
@@ -348,9 +377,12 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
 
   // observation normalisation: one FMA per entry with prepared coefficients (norm_fma, exenv_math.cuh); every
   // instantiation of this kernel (vector, fused-epilogue, generic) and the packed kernel use the same form
-  NormFma<T> nf[D];
+  NormFma<T> nf_thread[D];
+  if constexpr (!HOST_PRE) {
 #pragma unroll
-  for (int d = 0; d < D; ++d) nf[d] = make_normfma<T>(pn[2 * d], pn[2 * d + 1]);
+    for (int d = 0; d < D; ++d) nf_thread[d] = make_normfma<T>(pn[2 * d], pn[2 * d + 1]);
+  }
+  const NormFma<T> *nf = HOST_PRE ? hp.nf : nf_thread;
   T om_norm[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) om_norm[v] = Env::IS_PMSM ? norm_fma<T>(s0[v][D - 1], nf[D - 1]) : (T)0;
@@ -726,7 +758,8 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   const long threads = (x.batch + V - 1) / V;
   const int nthr = simtm_block_threads();
   const unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
-  kern<<<grid, nthr, smem, stream>>>(a, kp);
+  const SimTmHostPre<Env, T> hp = make_host_pre<Env, T>(kp);
+  kern<<<grid, nthr, smem, stream>>>(a, kp, hp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

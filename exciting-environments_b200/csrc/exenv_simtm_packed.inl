@@ -12,7 +12,8 @@
 // kernel of exenv_simtm.inl, which this file mirrors step for step.
 template <class Env, int SOLVER, int W, int V, bool EPI>
 __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
-    simtm_packed_kernel(const __grid_constant__ SimTmK<float> a, const __grid_constant__ KParams<float> kp) {
+    simtm_packed_kernel(const __grid_constant__ SimTmK<float> a, const __grid_constant__ KParams<float> kp,
+                        const __grid_constant__ SimTmHostPre<Env, float> hp) {
   using T = float;
   using P = f32x2;
   using EnvP = typename Env::template rebind<P>;
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   P pq[NP];
 #pragma unroll
   for (int i = 0; i < NP; ++i) pq[i] = P(p[i]);
-  const typename EnvP::Pre pre = EnvP::precompute(pq);
+  const typename EnvP::Pre pre = EnvP::from_scalar(hp.pre);  // host-prepared scalars, broadcast operands
   const P *pn = pq + Env::NSTATIC;
   typename EnvP::Aux aux{};
 
@@ -53,7 +54,10 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   }
   NormFma<P> nf[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) nf[d] = make_normfma<P>(pn[2 * d], pn[2 * d + 1]);
+  for (int d = 0; d < D; ++d) {
+    nf[d].c1 = P(hp.nf[d].c1);
+    nf[d].c0 = P(hp.nf[d].c0);
+  }
 
   // ---- window of prepared ZOH actions (see exenv_simtm.inl) ------------------------------------------------------
   const int q_max = (int)a.n_actions - 1;
@@ -321,7 +325,8 @@ static int launch_simtm_packed_v(const SimTmK<float> &a, const KParams<float> &k
   const long threads = (batch + V - 1) / V;
   const int nthr = simtm_block_threads();
   const unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
-  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, nthr, 0, stream>>>(a, kp);
+  const SimTmHostPre<Env, float> hp = make_host_pre<Env, float>(kp);
+  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, nthr, 0, stream>>>(a, kp, hp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
