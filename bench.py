@@ -135,8 +135,11 @@ def bind_to_gpu_numa_node(dev_index):
 
 # ---- clocks ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi polled every 50 ms from before the warm-up (its start-up can take longer than a short timed region);
+    stop(t0, t1) keeps the samples whose own timestamps fall inside the timed region [t0, t1] (wall clock)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -147,28 +150,46 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.06)  # one more polling period: the last sample of the region is on its way
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        rows = []
+        for line in open(self.f.name):
+            r = line.strip().split(", ")
+            if len(r) < 8 or not r[1].replace(".", "").isdigit():
+                continue
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = None
+            rows.append((ts, r[1:]))
         os.unlink(self.f.name)
-        sm = sorted(float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        inside = [r for ts, r in rows if ts is not None and t0 is not None and t0 - 0.02 <= ts <= t1 + 0.02]
+        window = "timed region"
+        if not inside:  # a region shorter than the polling period: the samples closest to it
+            after = [r for ts, r in rows if ts is None or t0 is None or ts >= t0 - 0.5]
+            inside, window = (after or [r for _, r in rows]), "nearest to the timed region"
+        sm = sorted(float(r[0]) for r in inside)
         if sm:
             out["sm_mhz"] = sm[len(sm) // 2]
-            out["sm_max_mhz"] = max(float(r[1]) for r in rows if len(r) >= 7)
+            out["sm_max_mhz"] = max(float(r[1]) for r in inside)
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            out["reasons"] = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in rows)]
+            out["reasons"] = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in inside)]
             out["samples"] = len(sm)
             out["sm_mhz_min"] = sm[0]
-            pw = [float(r[2]) for r in rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+            pw = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
             out["power_w_max"] = max(pw) if pw else None
+            out["window"] = window
         return out
 
 
@@ -256,19 +277,21 @@ def run_b200(args):
         def step():
             return env._sim_impl(env.env_properties, B, state, acts, TAU, TAU, out=out, layout=layout)
 
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         for _ in range(n_warm):
             step()
         barrier()
-        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         launches0 = ex.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
         e0.record()
         for _ in range(n_steps):
             step()
         e1.record()
         barrier()
+        t_wall1 = time.time()
         launches = ex.launch_count() - launches0
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
         elapsed = e0.elapsed_time(e1) * 1e-3
         t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
         if dist is not None:

@@ -274,9 +274,10 @@ __device__ __forceinline__ void staged_to_fields(const T *st, T omega_el, T *sv)
 // Measured per environment (profiles/README.md): PMSM 123 -> 96 registers (+13 %), acrobot fp64 +19 %, fp64
 // mass-spring-damper +7 %; pendulum and fluid tank lose 7-9 % (their allocation was already minimal and the constant-bank
 // operands lengthen the dependent chains), so they keep the per-thread preparation.
-template <class Env>
+// The bandwidth-bound Euler kernels lose 2-3 % as well: Tsit5 only.
+template <class Env, int SOLVER>
 constexpr bool simtm_use_host_pre() {
-  return Env::ID == 1 || Env::ID == 4 || Env::ID == 5;
+  return SOLVER == EXENV_TSIT5 && (Env::ID == 1 || Env::ID == 4 || Env::ID == 5);
 }
 template <class Env, typename T>
 struct SimTmHostPre {
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     load_env_params<Env, T, true>(kp, b, pl);
     p = pl;
   }
-  constexpr bool HOST_PRE = !PER_ENV && simtm_use_host_pre<Env>();
+  constexpr bool HOST_PRE = !PER_ENV && simtm_use_host_pre<Env, SOLVER>();
   typename Env::Pre pre_thread;
   if constexpr (!HOST_PRE) pre_thread = Env::precompute(p);
   const typename Env::Pre &pre = HOST_PRE ? hp.pre : pre_thread;

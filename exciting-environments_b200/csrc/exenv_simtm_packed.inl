@@ -30,7 +30,11 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   P pq[NP];
 #pragma unroll
   for (int i = 0; i < NP; ++i) pq[i] = P(p[i]);
-  const typename EnvP::Pre pre = EnvP::from_scalar(hp.pre);  // host-prepared scalars, broadcast operands
+  constexpr bool HOST_PRE = simtm_use_host_pre<Env, SOLVER>();  // host-prepared scalars, broadcast operands
+  typename EnvP::Pre pre_thread;
+  if constexpr (HOST_PRE) pre_thread = EnvP::from_scalar(hp.pre);
+  else pre_thread = EnvP::precompute(pq);
+  const typename EnvP::Pre &pre = pre_thread;
   const P *pn = pq + Env::NSTATIC;
   typename EnvP::Aux aux{};
 
@@ -55,8 +59,12 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   NormFma<P> nf[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    nf[d].c1 = P(hp.nf[d].c1);
-    nf[d].c0 = P(hp.nf[d].c0);
+    if constexpr (HOST_PRE) {
+      nf[d].c1 = P(hp.nf[d].c1);
+      nf[d].c0 = P(hp.nf[d].c0);
+    } else {
+      nf[d] = make_normfma<P>(pn[2 * d], pn[2 * d + 1]);
+    }
   }
 
   // ---- window of prepared ZOH actions (see exenv_simtm.inl) ------------------------------------------------------
