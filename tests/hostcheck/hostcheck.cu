@@ -143,6 +143,22 @@ static void sim_any(const ExenvDesc *d, const HcLut *lut, long B, long n_actions
            (T *const *)traj)
 }
 
+// exenv_math.cuh: the three normalisation forms on arrays -- norm_mm (the reference's expression, IEEE division),
+// norm_inv<true> (prepared reciprocal + correction: what the truncation flags are evaluated on) and norm_fma (one FMA:
+// what the time-major trajectory kernels return)
+template <typename T>
+static void norm_forms_t(long n, const T *x, T mn, T mx, T *o_mm, T *o_inv, T *o_fma, T *coef) {
+  const InvDiv<T> span = make_invdiv<T>(mx - mn);
+  const NormFma<T> nf = make_normfma<T>(mn, mx);
+  coef[0] = nf.c1;
+  coef[1] = nf.c0;
+  for (long i = 0; i < n; ++i) {
+    o_mm[i] = norm_mm<T>(x[i], mn, mx);
+    o_inv[i] = norm_inv<true, T>(x[i], mn, span);
+    o_fma[i] = norm_fma<T>(x[i], nf);
+  }
+}
+
 extern "C" {
 void hc_step(const ExenvDesc *d, const HcLut *lut, long B, const void *const *sin, const void *action,
              void *const *sout, void *obs, void *const *kout) {
@@ -156,6 +172,14 @@ void hc_sim(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, long n
   else sim_any<float>(d, lut, B, n_actions, n_save, n_steps, words, dts, thetas, sin, actions, traj);
 }
 // exenv_math.cuh: fmod_pos (exact C fmod without the iterative reduction) and wrap_pi on arrays
+void hc_norm_forms(long n, int is_f64, const void *x, double mn, double mx, void *o_mm, void *o_inv, void *o_fma,
+                   void *coef) {
+  if (is_f64)
+    norm_forms_t<double>(n, (const double *)x, mn, mx, (double *)o_mm, (double *)o_inv, (double *)o_fma, (double *)coef);
+  else
+    norm_forms_t<float>(n, (const float *)x, (float)mn, (float)mx, (float *)o_mm, (float *)o_inv, (float *)o_fma,
+                        (float *)coef);
+}
 void hc_fmod_two_pi(long n, int is_f64, const void *x, void *fmod_out, void *wrap_out) {
   for (long i = 0; i < n; ++i) {
     if (is_f64) {

@@ -157,3 +157,35 @@ def test_fast_fmod_is_exact(hostcheck_lib, dtype):
     assert np.array_equal(np.isnan(f), nan) and np.array_equal(f[~nan].view(u), ref[~nan].view(u))
     nanw = np.isnan(wref)
     assert np.array_equal(np.isnan(w), nanw) and np.array_equal(w[~nanw], wref[~nanw])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_normalisation_forms(hostcheck_lib, dtype):
+    """exenv_math.cuh: norm_inv<true> (prepared reciprocal + one correction; the form the truncation flags are evaluated
+    on) is bit-identical to the reference's 2 (x - min) / (max - min) - 1 with an IEEE division, flags included; norm_fma
+    (one FMA, what the time-major kernels return) stays within 3 ulp of 1 of it, its offset is exactly 0 / -1 for
+    symmetric / zero-based ranges, and it is exact at 0 and at the lower edge of a zero-based range."""
+    rng = np.random.default_rng(5)
+    eps = np.finfo(dtype).eps
+    for mn, mx in [(-np.pi, np.pi), (-10, 10), (-15, 15), (0, 3), (0, 0.2), (-400, 0), (-0.37, 0.37), (-41, 41),
+                   (-3.3, 7.9), (1.5, 2.5)]:
+        lo, hi = dtype(mn), dtype(mx)
+        edge = np.array([lo, hi, np.nextafter(lo, dtype(-np.inf)), np.nextafter(hi, dtype(np.inf)), 0.0, -0.0,
+                         lo * dtype(1.001) if lo != 0 else dtype(-1e-3), hi * dtype(1.001)], dtype)
+        x = np.concatenate([edge, rng.uniform(float(lo) - 0.1 * float(hi - lo), float(hi) + 0.1 * float(hi - lo),
+                                              100000).astype(dtype)])
+        o = [np.empty_like(x) for _ in range(3)]
+        coef = np.empty(2, dtype)
+        hostcheck_lib.hc_norm_forms(C.c_long(x.size), C.c_int(dtype == np.float64), C.c_void_p(x.ctypes.data),
+                                    C.c_double(float(lo)), C.c_double(float(hi)), *[C.c_void_p(a.ctypes.data) for a in o],
+                                    C.c_void_p(coef.ctypes.data))
+        ref = dtype(2) * (x - lo) / (hi - lo) - dtype(1)
+        assert ref.dtype == dtype
+        assert np.array_equal(o[0], ref)
+        assert np.array_equal(o[1], ref), (mn, mx)                      # correctly rounded: same value, same flags
+        assert np.array_equal(np.abs(o[1]) > 1, np.abs(ref) > 1)
+        assert np.max(np.abs(o[2] - ref)) <= 3 * eps * max(1.0, float(np.max(np.abs(ref)))), (mn, mx)
+        if mn == -mx:
+            assert coef[1] == 0 and o[2][4] == 0
+        if mn == 0:
+            assert coef[1] == -1 and o[2][0] == -1
