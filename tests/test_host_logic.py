@@ -107,3 +107,51 @@ def test_json_fixture_loader_round_trip(excenvs, tmp_path):
     env = ex.EnvironmentRegistry.PMSM.make(tau=tau, static_params=params, physical_normalizations=pn,
                                            action_normalizations=an)
     assert env.env_properties.static_params.u_dc == 400
+
+
+def test_bench_clock_sampler_keeps_the_samples_of_the_timed_region(tmp_path):
+    """bench.py: nvidia-smi is polled from before the warm-up; only samples whose own timestamps fall inside the timed
+    region count for the reported clocks / throttle reasons; a region shorter than the polling period falls back to the
+    nearest samples."""
+    import datetime
+    import importlib.util
+    import sys
+    import time
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("bench_under_test", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+
+    class Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            pass
+
+    def sampler(rows):
+        cs = bench.ClockSampler.__new__(bench.ClockSampler)
+        f = tmp_path / f"smi{len(rows)}.csv"
+        f.write_text("".join(rows))
+        cs.f = open(f, "r+")
+        cs.p = Done()
+        return cs
+
+    now = time.time()
+
+    def row(dt, mhz, cap):
+        ts = datetime.datetime.fromtimestamp(now + dt).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return f"{ts}, {mhz}, 1965, 400.5, Not Active, Not Active, Not Active, {cap}\n"
+
+    rows = [row(0.00, 1965, "Not Active"), row(0.05, 1935, "Not Active"), row(0.10, 1905, "Active"),
+            row(0.15, 1965, "Not Active"), "garbage line\n"]
+    out = sampler(rows).stop(now + 0.04, now + 0.11)
+    assert out["samples"] == 2 and out["sm_mhz_min"] == 1905.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region" and out["power_w_max"] == 400.5
+    out = sampler(rows[:2]).stop(now + 0.20, now + 0.21)  # nothing inside: nearest samples, said so
+    assert out["samples"] == 2 and out["window"].startswith("nearest") and out["reasons"] == []
