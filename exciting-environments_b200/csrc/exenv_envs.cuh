@@ -132,11 +132,7 @@ struct Pendulum {
   template <bool FAST>
   EX_HD static void rhs(const T *y, const T *u, const T *, const Pre &q, const Aux &, T *dy) {
     dy[0] = y[1];
-    if constexpr (FAST) {
-      T sn, cs;
-      sincos_fast(y[0], &sn, &cs);  // the cosine is dead code: only the shared reduction and the sine polynomial remain
-      dy[1] = div_mul<T>(u[0] + q.lmg * sn, q.ml2);
-    }
+    if constexpr (FAST) dy[1] = div_mul<T>(u[0] + q.lmg * Mth<T>::sin(y[0]), q.ml2);
     else dy[1] = div_inv<false, T>(u[0] + q.lmg * Mth<T>::sin(y[0]), q.ml2);
   }
   EX_HD static void post(T *y) { y[0] = wrap_pi<T>(y[0]); }  // :188, :241
@@ -277,8 +273,7 @@ struct CartPole {
     const T mu_p = p[0], mu_c = p[1], l = p[2], m_p = p[3], g = p[5];
     const T v = y[1], th = y[2], om = y[3];
     T s, c;
-    if constexpr (FAST) sincos_fast(th, &s, &c);
-    else Mth<T>::sincos(th, &s, &c);
+    Mth<T>::sincos(th, &s, &c);
     const T sg = sign_of<T>(v);
     T d_om, d_v;
     if constexpr (FAST) {  // quotients by parameters as products with the prepared reciprocal, the one state-dependent
@@ -319,8 +314,7 @@ struct Acrobot {
     const T g = p[0], l1 = p[1], m1 = p[3], m2 = p[4], lc1 = p[5], lc2 = p[6], I1 = p[7], I2 = p[8];
     const T th1 = y[0], th2 = y[1], om1 = y[2], om2 = y[3];
     T s2, c2;
-    if constexpr (FAST) sincos_fast(th2, &s2, &c2);
-    else Mth<T>::sincos(th2, &s2, &c2);
+    Mth<T>::sincos(th2, &s2, &c2);
     const T d11 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2 + (T)2 * l1 * lc2 * c2) + I1 + I2;
     const T d12 = m2 * (lc2 * lc2 + l1 * lc2 * c2) + I2;
     const T d22 = m2 * (lc2 * lc2) + I2;
@@ -331,7 +325,7 @@ struct Acrobot {
                            // cosines (the reference's arguments carry the rounding of x + fl(pi/2), i.e. a few 1e-7 of
                            // noise in fp32; the values agree to that level)
       T s1, c1;
-      sincos_fast(th1, &s1, &c1);
+      Mth<T>::sincos(th1, &s1, &c1);
       ca = -s1;
       cb = -(s1 * c2 + c1 * s2);
     } else {

@@ -54,34 +54,6 @@ struct Mth<double> {
   static EX_HD double abs(double x) { return ::fabs(x); }
 };
 
-// sin and cos of a moderate argument (|x| <= 64: angles are wrapped to [-pi, pi) at every save) for the FAST
-// right-hand sides: ONE three-term Cody-Waite reduction by pi/2 shared by both results, then the two degree-7 / degree-8
-// minimax polynomials of Cephes sinf / cosf on [-pi/4, pi/4] (each within about 1 ulp; CUDA's own sinf / cosf are
-// specified to 2 ulp).  About 20 instructions for the pair instead of about 40 for sincosf.  Larger arguments, inf and
-// nan take libm.  Plain fmaf / rintf: the same code runs in the CPU test harness.
-EX_HD void sincos_fast(float x, float *s, float *c) {
-  if (!(::fabsf(x) <= 64.0f)) {
-    Mth<float>::sincos(x, s, c);
-    return;
-  }
-  const float kf = ::rintf(x * 0.63661977236758134f);  // nearest integer to x / (pi/2)
-  const int k = (int)kf;
-  float r = ::fmaf(kf, -1.5703125f, x);  // pi/2 = 1.5703125 + 4.837512969970703125e-4 + 7.54978995489188216e-8 + ...
-  r = ::fmaf(kf, -4.837512969970703125e-4f, r);
-  r = ::fmaf(kf, -7.54978995489188216e-8f, r);
-  const float z = r * r;
-  const float ps = ::fmaf(::fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
-  const float sr = ::fmaf(ps * z, r, r);
-  const float pc = ::fmaf(::fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
-  const float cr = ::fmaf(z * z, pc, ::fmaf(-0.5f, z, 1.0f));
-  float so = (k & 1) ? cr : sr, co = (k & 1) ? sr : cr;
-  if (k & 2) so = -so;
-  if ((k + 1) & 2) co = -co;
-  *s = so;
-  *c = co;
-}
-EX_HD void sincos_fast(double x, double *s, double *c) { Mth<double>::sincos(x, s, c); }
-
 template <typename T>
 EX_HD T nan_of() {
   return (T)NAN;
