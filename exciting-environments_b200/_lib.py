@@ -16,6 +16,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("EXENV_B200_LIB") or (_PKG / "lib" / "libexenv_b200.so"))
 HEADER_PATH = _PKG.parent / "include" / "exenv_b200.h"
 
+ABI_VERSION = 3
 MAX_PARAMS, MAX_CONTROL, MAX_PHYS, MAX_ODE = 32, 8, 8, 4
 EULER, TSIT5 = 0, 1
 F32, F64 = 0, 1
@@ -91,7 +92,7 @@ class ExenvResetArgs(C.Structure):
 SYMBOLS = [
     "exenv_abi_version", "exenv_last_error", "exenv_env_dims", "exenv_launch_count", "exenv_plan_create",
     "exenv_plan_destroy", "exenv_step", "exenv_sim_ahead_shape", "exenv_sim_ahead", "exenv_sim_ahead_host",
-    "exenv_reset_pack", "exenv_schedule_build", "exenv_epilogue",
+    "exenv_reset_pack", "exenv_schedule_build", "exenv_epilogue", "exenv_trunc_thresholds",
 ]
 
 
@@ -133,7 +134,9 @@ def lib():
         L.exenv_schedule_build.argtypes = [C.POINTER(ExenvDesc), C.c_int64, C.c_double, C.c_double, C.c_int32,
                                            C.POINTER(ExenvScheduleInfo), C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
-        assert L.exenv_abi_version() == 2
+        L.exenv_trunc_thresholds.argtypes = [C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double)]
+        assert L.exenv_abi_version() == ABI_VERSION, "libexenv_b200.so was built from another header: rebuild it"
         _lib = L
     return _lib
 

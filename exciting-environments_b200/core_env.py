@@ -208,15 +208,42 @@ class CoreEnvironment:
         _lib.check(_lib.lib().exenv_plan_create(C.byref(desc), self.device.index or 0, C.byref(handle)))
         return _Plan(handle, keep)
 
+    _PLAN_CACHE_SIZE = 16
+
+    def _props_key(self, env_properties, batch):
+        """Cache key of a plan by VALUE: scalar slots by their float value, per-environment arrays by identity of the
+        array object (the entry keeps a strong reference, so the id cannot be recycled while the entry lives) together
+        with its data pointer and shape."""
+        key, keep = [], []
+        for v in self._param_slots(env_properties):
+            if hasattr(v, "shape") and len(v.shape) >= 1 and v.shape[0] == batch:
+                ptr = v.data_ptr() if isinstance(v, torch.Tensor) else v.__array_interface__["data"][0]
+                key.append(("arr", id(v), ptr, tuple(v.shape), str(v.dtype)))
+                keep.append(v)
+            else:
+                key.append(None if v is None else float(v))
+        return tuple(key), keep
+
     def _plan(self, env_properties=None, batch=None):
         if env_properties is None or env_properties is self.env_properties:
-            key, env_properties, batch = "self", self.env_properties, self.batch_size
+            env_properties, batch = self.env_properties, self.batch_size
         else:
-            key, batch = ("props", id(env_properties)), (batch or 1)
-        key = (key, self._solver_id, self.dtype, tuple(self.control_state), self.time_rule)
-        if key not in self._plans:
-            self._plans[key] = self._make_plan(env_properties, batch)
-        return self._plans[key]
+            batch = batch or 1
+        pkey, keep = self._props_key(env_properties, batch)
+        key = (pkey, batch, float(self.tau), self._solver_id, self.dtype, tuple(self.control_state), self.time_rule,
+               self._plan_extra_key(env_properties))
+        plan = self._plans.pop(key, None)
+        if plan is None:
+            plan = self._make_plan(env_properties, batch)
+            plan.keep_key = keep
+            while len(self._plans) >= self._PLAN_CACHE_SIZE:  # least recently used first (dicts keep insertion order)
+                self._plans.pop(next(iter(self._plans)))
+        self._plans[key] = plan  # (re-)inserted last: most recently used
+        return plan
+
+    def _plan_extra_key(self, env_properties):
+        """Hook for PMSM (saturated flag, motor LUT identity)."""
+        return None
 
     # ---- small cached constants -----------------------------------------------------------------------------------
     def _constant(self, kind, B):

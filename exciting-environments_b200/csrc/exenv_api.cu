@@ -596,6 +596,33 @@ int exenv_schedule_build(const ExenvDesc *desc, int64_t n_actions, double obs_st
   return EXENV_OK;
 }
 
+int exenv_trunc_thresholds(int32_t dtype, double mn, double mx, double *lo_last, double *hi_first) {
+  if (!lo_last || !hi_first) {
+    set_error("exenv_trunc_thresholds: NULL argument");
+    return EXENV_ERR_NULL;
+  }
+  bool ok;
+  if (dtype == EXENV_F64) {
+    TruncThr<double> t;
+    ok = make_trunc_thresholds<double>(mn, mx, t);
+    *lo_last = t.lo_last;
+    *hi_first = t.hi_first;
+  } else if (dtype == EXENV_F32) {
+    TruncThr<float> t;
+    ok = make_trunc_thresholds<float>((float)mn, (float)mx, t);
+    *lo_last = t.lo_last;
+    *hi_first = t.hi_first;
+  } else {
+    set_error("exenv_trunc_thresholds: bad dtype %d", dtype);
+    return EXENV_ERR_INVALID;
+  }
+  if (!ok) {
+    set_error("exenv_trunc_thresholds: degenerate range [%g, %g]", mn, mx);
+    return EXENV_ERR_INVALID;
+  }
+  return EXENV_OK;
+}
+
 static int validate_sim(const ExenvPlan *plan, const ExenvSimArgs *a) {
   if (!plan || !a) {
     set_error("exenv_sim_ahead: NULL plan/args");

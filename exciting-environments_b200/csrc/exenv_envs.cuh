@@ -605,8 +605,9 @@ EX_HD bool trunc_entry(int i, const T *s, const T *obs_full, const T *p) {
   if constexpr (Env::ID == 2) {
     return false;
   } else if constexpr (Env::IS_PMSM) {
+    // i_s = sqrt(i_d_norm**2 + i_q_norm**2) > 1: un-fused squares and sum (bit-exact flag whatever -fmad says)
     const T idn = norm_field<Env, T>(3, s, p), iqn = norm_field<Env, T>(4, s, p);
-    return Mth<T>::sqrt(idn * idn + iqn * iqn) > (T)1;
+    return Mth<T>::sqrt(add_rn(mul_rn(idn, idn), mul_rn(iqn, iqn))) > (T)1;
   } else {
     return Mth<T>::abs(obs_full[i]) > (T)1;
   }

@@ -5,6 +5,8 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <limits>
 
 #if defined(__CUDACC__)
 #define EX_HD __host__ __device__ __forceinline__
@@ -150,6 +152,111 @@ EX_HD NormFma<T> make_normfma(T mn, T mx) {
 template <typename T>
 EX_HD T norm_fma(T x, const NormFma<T> &n) {
   return fma_(x, n.c1, n.c0);
+}
+
+// Single IEEE operations the compiler must not contract into a fused multiply-add, whatever -fmad says: the truncation
+// flags are bit-exact statements about un-fused expressions (the host harness is compiled with -ffp-contract=off).
+EX_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+EX_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+EX_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+EX_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+
+// truncated = abs(2 (x - min) / (max - min) - 1) > 1 as two comparisons.  Every operation of the reference expression
+// is a monotone (non-decreasing) function of x under round-to-nearest, so the flag is "x >= hi_first or x <= lo_last"
+// for two thresholds found ONCE on the host by bisection over the floating-point numbers with the reference expression
+// itself (make_trunc_thresholds): bit-exact by construction, two compares instead of a correctly rounded division per
+// observation entry.  NaN compares false on both sides, like abs(NaN) > 1.
+template <typename T>
+struct TruncThr {
+  T lo_last, hi_first;
+};
+template <typename T>
+EX_HD bool trunc_by_threshold(T x, const TruncThr<T> &t) {
+  return (x >= t.hi_first) || (x <= t.lo_last);
+}
+namespace detail {
+inline uint32_t ord_of(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+inline float of_ord(uint32_t o, float) {
+  const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint64_t ord_of(double f) {
+  uint64_t u;
+  memcpy(&u, &f, 8);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+inline double of_ord(uint64_t o, double) {
+  const uint64_t u = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
+  double f;
+  memcpy(&f, &u, 8);
+  return f;
+}
+}  // namespace detail
+// Host only (compiled with -ffp-contract=off).  Returns false when the range is degenerate (span not a positive finite
+// number): the caller then takes the path that evaluates the expression itself.
+template <typename T>
+inline bool make_trunc_thresholds(T mn, T mx, TruncThr<T> &out) {
+  const T span = mx - mn;
+  if (!(span > (T)0) || !(span < std::numeric_limits<T>::infinity()) || mn != mn) return false;
+  auto g = [&](T x) -> T {
+    volatile T d = x - mn;
+    volatile T n = (T)2 * d;
+    volatile T q = n / span;
+    volatile T r = q - (T)1;
+    return r;
+  };
+  const T inf = std::numeric_limits<T>::infinity();
+  auto lo_o = detail::ord_of(-inf), hi_o = detail::ord_of(inf);
+  using U = decltype(lo_o);
+  {  // smallest x with g(x) > 1 (exists: g(+inf) = +inf; g(-inf) = -inf)
+    U a = lo_o, b = hi_o;  // g(a) > 1 false, g(b) > 1 true
+    while (b - a > 1) {
+      const U m = a + (b - a) / 2;
+      if (g(detail::of_ord(m, (T)0)) > (T)1) b = m;
+      else a = m;
+    }
+    out.hi_first = detail::of_ord(b, (T)0);
+  }
+  {  // largest x with g(x) < -1
+    U a = lo_o, b = hi_o;  // g(a) < -1 true, g(b) < -1 false
+    while (b - a > 1) {
+      const U m = a + (b - a) / 2;
+      if (g(detail::of_ord(m, (T)0)) < (T)-1) a = m;
+      else b = m;
+    }
+    out.lo_last = detail::of_ord(a, (T)0);
+  }
+  return true;
 }
 
 // C fmod(x, y) for y > 0, exactly, without libm's iterative reduction when the quotient is moderate (angles: a few

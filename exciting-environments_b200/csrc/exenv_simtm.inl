@@ -283,14 +283,29 @@ template <class Env, typename T>
 struct SimTmHostPre {
   typename Env::Pre pre;
   NormFma<T> nf[Env::D];
+  TruncThr<T> thr[Env::D];  // truncation flags of the fused epilogue as threshold compares (exenv_math.cuh)
 };
 template <class Env, typename T>
-static SimTmHostPre<Env, T> make_host_pre(const KParams<T> &kp) {
+static SimTmHostPre<Env, T> make_host_pre(const KParams<T> &kp, bool *thr_ok = nullptr) {
   SimTmHostPre<Env, T> h;
   h.pre = Env::precompute(kp.v);
   const T *pn = kp.v + Env::NSTATIC;
-  for (int d = 0; d < Env::D; ++d) h.nf[d] = make_normfma<T>(pn[2 * d], pn[2 * d + 1]);
+  bool ok = true;
+  for (int d = 0; d < Env::D; ++d) {
+    h.nf[d] = make_normfma<T>(pn[2 * d], pn[2 * d + 1]);
+    h.thr[d].lo_last = h.thr[d].hi_first = (T)NAN;
+    if (thr_ok && !Env::IS_PMSM && Env::ID != 2) ok = make_trunc_thresholds<T>(pn[2 * d], pn[2 * d + 1], h.thr[d]) && ok;
+  }
+  if (thr_ok) *thr_ok = ok;
   return h;
+}
+// Shared-parameter ranges for which the threshold form of the truncation flags exists (every sane range)
+template <class Env, typename T>
+static bool simtm_thresholds_ok(const ExenvPlan &plan) {
+  if (plan.per_env) return false;
+  bool ok = true;
+  make_host_pre<Env, T>(make_kparams<T>(plan), &ok);
+  return ok;
 }
 
 template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
@@ -390,13 +405,12 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   // The truncation flags (EPI / GENERIC instantiations only) are bit-exact statements about the REFERENCE's observation,
   // abs(2 (x - min) / (max - min) - 1) > 1, so they are evaluated on the correctly rounded quotient (div_inv), not on
   // the one-FMA value that is returned: a state exactly on the edge of its range must not be flagged.
-  InvDiv<T> sdiv[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<T>(pn[2 * d + 1] - pn[2 * d]);
+  // GENERIC: the reference expression itself (IEEE division); EPI: threshold compares prepared on the host with that
+  // expression (hp.thr, exenv_math.cuh: make_trunc_thresholds) -- the same flags, two compares per entry.
   auto obs_for_flags = [&](const T *sv, T *obx) {
     if constexpr (!Env::IS_PMSM) {  // PMSM's flag is computed from the state (trunc_entry)
 #pragma unroll
-      for (int o = 0; o < O; ++o) obx[o] = norm_inv<true, T>(sv[o], pn[2 * o], sdiv[o]);
+      for (int o = 0; o < O; ++o) obx[o] = norm_mm<T>(sv[o], pn[2 * o], pn[2 * o + 1]);
     }
   };
   T rf[D];
@@ -487,11 +501,11 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   uint8_t *tmp = EPI ? a.term + b : nullptr;
   auto flags_fast = [&](const T *sv, const T *, uint8_t *tr, uint8_t &te) {  // control_state == []
     bool t0 = false;
-    T obx[O];
-    obs_for_flags(sv, obx);
 #pragma unroll
     for (int i = 0; i < NT0; ++i) {
-      const bool tv = trunc_entry<Env, T>(i, sv, obx, p);
+      bool tv;
+      if constexpr (Env::IS_PMSM || Env::ID == 2) tv = trunc_entry<Env, T>(i, sv, sv, p);  // from the state / constant
+      else tv = trunc_by_threshold<T>(sv[i], hp.thr[i]);
       if (i == 0) t0 = tv;
       tr[i] = tv;
     }
@@ -759,7 +773,12 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   const long threads = (x.batch + V - 1) / V;
   const int nthr = simtm_block_threads();
   const unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
-  const SimTmHostPre<Env, T> hp = make_host_pre<Env, T>(kp);
+  bool thr_ok = true;
+  const SimTmHostPre<Env, T> hp = make_host_pre<Env, T>(kp, EPI ? &thr_ok : nullptr);
+  if (!thr_ok) {
+    set_error("sim_ahead (time-major): degenerate normalisation range for the fused truncation flags");
+    return EXENV_ERR_INVALID;
+  }
   kern<<<grid, nthr, smem, stream>>>(a, kp, hp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
@@ -880,6 +899,7 @@ static int simtm_dispatch2(const ExenvPlan &plan, const ExenvSimArgs &x, const S
   // with aligned vector stores
   const bool epi_any = x.reward || x.truncated || x.terminated, epi_all = x.reward && x.truncated && x.terminated;
   bool generic = plan.desc.n_control > 0 || (epi_any && !epi_all);
+  if (epi_all && !generic) generic = !simtm_thresholds_ok<Env, T>(plan);  // degenerate ranges: evaluate the expression
   for (int d = 0; d < Env::D; ++d) generic |= x.traj[d] == nullptr;
   {
     const size_t row_bytes = (size_t)Env::O * sizeof(T);

@@ -134,17 +134,13 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
     for (int o = 0; o < O; ++o) ob[o] = norm_fma<P>(sv[o], nf[o]);
   };
   // flags: from the correctly rounded reference-form observation (see exenv_simtm.inl), per lane
-  InvDiv<T> sdiv[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) sdiv[d] = make_invdiv<T>(p[Env::NSTATIC + 2 * d + 1] - p[Env::NSTATIC + 2 * d]);
   auto flags_lane = [&](const T *sv, const T *, uint8_t *tr, uint8_t &te) {  // control_state == []
     bool t0 = false;
-    T obx[O];
-#pragma unroll
-    for (int o = 0; o < O; ++o) obx[o] = norm_inv<true, T>(sv[o], p[Env::NSTATIC + 2 * o], sdiv[o]);
 #pragma unroll
     for (int i = 0; i < NT0; ++i) {
-      const bool tv = trunc_entry<Env, T>(i, sv, obx, p);
+      bool tv;
+      if constexpr (Env::ID == 2) tv = false;  // fluid tank: constant (fluid_tank_env.py:323-326)
+      else tv = trunc_by_threshold<T>(sv[i], hp.thr[i]);
       if (i == 0) t0 = tv;
       tr[i] = tv;
     }
@@ -333,7 +329,12 @@ static int launch_simtm_packed_v(const SimTmK<float> &a, const KParams<float> &k
   const long threads = (batch + V - 1) / V;
   const int nthr = simtm_block_threads();
   const unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
-  const SimTmHostPre<Env, float> hp = make_host_pre<Env, float>(kp);
+  bool thr_ok = true;
+  const SimTmHostPre<Env, float> hp = make_host_pre<Env, float>(kp, EPI ? &thr_ok : nullptr);
+  if (!thr_ok) {
+    set_error("sim_ahead (time-major, packed): degenerate normalisation range for the fused truncation flags");
+    return EXENV_ERR_INVALID;
+  }
   simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, nthr, 0, stream>>>(a, kp, hp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();

@@ -234,6 +234,9 @@ class PMSM(CoreEnvironment):
         self._action_description = ["u_d", "u_q"]
         self._obs_description = ["i_d", "i_q", "cos_eps", "sin_eps", "omega_el", "torque", "u_d_buffer", "u_q_buffer"]
 
+    def _plan_extra_key(self, env_properties):
+        return (bool(self.saturated), id(self._lut))
+
     def _desc_extra(self, desc, keep):
         import ctypes as C
 

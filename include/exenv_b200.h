@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EXENV_ABI_VERSION 2
+#define EXENV_ABI_VERSION 3
 #define EXENV_MAX_PARAMS 32
 #define EXENV_MAX_CONTROL 8
 #define EXENV_MAX_PHYS 8
@@ -207,6 +207,12 @@ typedef struct ExenvScheduleInfo {
 int exenv_schedule_build(const ExenvDesc *desc, int64_t n_actions, double obs_stepsize, double action_stepsize,
                          int32_t tile_steps, ExenvScheduleInfo *info, uint64_t *words, double *dt, double *theta,
                          int32_t *tiles);
+
+/* Host-only diagnostic (needs no CUDA device): the two thresholds the fused trajectory epilogue compares a state with
+ * instead of evaluating `abs(2 * (x - min) / (max - min) - 1) > 1` (generate_truncated, e.g. pendulum_env.py:381-385 with
+ * utils.py:13-14): the flag is `x >= *hi_first || x <= *lo_last`, found by bisection over the floating-point numbers of
+ * `dtype` with the reference expression itself.  Returns EXENV_ERR_INVALID for a degenerate range. */
+int exenv_trunc_thresholds(int32_t dtype, double min, double max, double *lo_last, double *hi_first);
 
 /* ---- vmap_reset state packing / generate_state_from_observation ----------------------------------------------- */
 typedef enum ExenvResetMode {

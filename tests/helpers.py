@@ -123,3 +123,50 @@ def traj_err(a, b, scale):
     denom = np.maximum(np.max(np.abs(b.reshape(b.shape[0], -1)), axis=1), scale)
     err = np.max(np.abs(a - b).reshape(b.shape[0], -1), axis=1)
     return float(np.max(err / denom))
+
+
+def flags_from_states(orc, leaves, refs=None):
+    """The reference's truncated flags, evaluated with IEEE NumPy arithmetic in the oracle's dtype on GIVEN physical
+    states (any leading shape): `abs(generate_observation(state)) > 1` (pendulum_env.py:311-329, 381-385 and the same
+    lines of the other environments; normalisation utils.py:13-14), the fluid tank's constant `[0]`
+    (fluid_tank_env.py:323-326), PMSM `sqrt(i_d_norm**2 + i_q_norm**2)[None] > 1` (pmsm_env.py:972-979).
+    Returns uint8 of shape leaves[0].shape + (n_trunc,).  This is what the kernels' flags are compared with, bit for
+    bit, on the states the kernels themselves return."""
+    T = orc.dtype
+    names = list(orc.spec.phys)
+
+    def norm(x, name):
+        lo, hi = orc.pn[name]
+        lo, hi = np.asarray(lo, T), np.asarray(hi, T)
+        if lo.ndim:  # per-environment ranges: broadcast over trailing (time) axes
+            lo = lo.reshape(lo.shape + (1,) * (np.ndim(x) - 1))
+            hi = hi.reshape(hi.shape + (1,) * (np.ndim(x) - 1))
+        x = np.asarray(x, T)
+        out = T(2) * (x - lo) / (hi - lo) - T(1)
+        assert out.dtype == T
+        return out
+
+    lv = dict(zip(names, leaves))
+    if orc.env == "fluid_tank":
+        return np.zeros(np.shape(leaves[0]) + (1,), np.uint8)
+    if orc.env == "pmsm":
+        idn, iqn = norm(lv["i_d"], "i_d"), norm(lv["i_q"], "i_q")
+        i_s = np.sqrt(idn * idn + iqn * iqn)
+        return (i_s > T(1)).astype(np.uint8)[..., None]
+    cols = [np.abs(norm(lv[n], n)) > T(1) for n in names]
+    if refs is not None:
+        rv = dict(zip(names, refs))
+        for n in orc.control_state:
+            r = np.asarray(rv[n], T)
+            if r.ndim < np.ndim(leaves[0]):
+                r = r.reshape(r.shape + (1,) * (np.ndim(leaves[0]) - r.ndim))
+            cols.append(np.broadcast_to(np.abs(norm(r, n)) > T(1), np.shape(leaves[0])))
+    return np.stack(cols, axis=-1).astype(np.uint8)
+
+
+def ulp_err(a, b, dtype):
+    """max |a - b| in units of the last place of b (floor: the smallest normal scale of interest is b itself)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    eps = np.finfo(dtype).eps
+    denom = np.maximum(np.abs(b), np.finfo(dtype).tiny) * eps
+    return float(np.max(np.abs(a - b) / denom)) if a.size else 0.0

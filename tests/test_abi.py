@@ -20,7 +20,7 @@ def test_header_symbols_are_exported(excenvs):
     lib = L.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.exenv_abi_version() == 2
+    assert lib.exenv_abi_version() == excenvs._lib.ABI_VERSION == 3
     exported = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
     for sym in declared:
         assert f" T {sym}" in exported

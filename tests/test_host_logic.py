@@ -155,3 +155,94 @@ def test_bench_clock_sampler_keeps_the_samples_of_the_timed_region(tmp_path):
     assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region" and out["power_w_max"] == 400.5
     out = sampler(rows[:2]).stop(now + 0.20, now + 0.21)  # nothing inside: nearest samples, said so
     assert out["samples"] == 2 and out["window"].startswith("nearest") and out["reasons"] == []
+
+
+def test_plan_cache_is_keyed_by_parameter_values(excenvs, monkeypatch):
+    """The plan cache must not confuse two EnvProperties objects that happen to share an id() after garbage collection,
+    must notice reassigned / mutated properties and tau, and stays bounded (LRU)."""
+    ex = excenvs
+    env = ex.MassSpringDamper(batch_size=4, dtype=torch.float32, device="cpu")
+    made = []
+
+    class FakePlan:
+        def __init__(self, props):
+            self.k = props.static_params.k
+
+    def fake_make(self, props, batch):
+        made.append((props.static_params.k, batch, self.tau))
+        return FakePlan(props)
+
+    monkeypatch.setattr(type(env), "_make_plan", fake_make)
+    p0 = env._plan()
+    assert env._plan() is p0 and len(made) == 1
+    # a parameter sweep building fresh EnvProperties per call: every distinct value gets its own plan, equal values
+    # share one, whatever id() the temporaries have
+    for k in (50.0, 60.0, 50.0, 70.0):
+        props = env.EnvProperties(physical_normalizations=env.env_properties.physical_normalizations,
+                                  action_normalizations=env.env_properties.action_normalizations,
+                                  static_params=env.StaticParams(d=1, k=k, m=1))
+        assert env._plan(props, 1).k == k
+        del props
+    assert [m[0] for m in made] == [100, 50.0, 60.0, 70.0]
+    # in-place mutation of the environment's own properties and a new tau are noticed
+    env.env_properties.static_params.k = 123.0
+    assert env._plan().k == 123.0
+    env.tau = 2e-4
+    env._plan()
+    assert made[-1] == (123.0, 4, 2e-4)
+    # per-environment arrays: keyed by the array object
+    arr = np.full(4, 9.0, np.float32)
+    env.env_properties.static_params.k = arr
+    a1 = env._plan()
+    assert env._plan() is a1
+    env.env_properties.static_params.k = arr.copy()
+    assert env._plan() is not a1
+    # bounded
+    for k in range(40):
+        env.env_properties.static_params.k = float(k)
+        env._plan()
+    assert len(env._plans) <= env._PLAN_CACHE_SIZE
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_truncation_thresholds_reproduce_the_reference_expression(excenvs, dtype):
+    """The fused trajectory epilogue flags `abs(2 (x - min) / (max - min) - 1) > 1` by two threshold compares prepared on
+    the host (exenv_trunc_thresholds).  They must reproduce the reference expression (IEEE NumPy, utils.py:13-14 +
+    pendulum_env.py:381-385) for every float: checked on the neighbours of both thresholds, the range ends, zeros,
+    infinities, NaN and random states, for default and awkward ranges."""
+    import ctypes as C
+
+    L = excenvs._lib
+    T = dtype
+    rng = np.random.default_rng(3)
+    ranges = [(-math.pi, math.pi), (-10, 10), (0, 3), (-2.4, 2.4), (-8, 8), (-250, 0), (-0.37, 1.3), (1e-3, 7.0),
+              (-41.0, -3.0), (5.0, 5.0000005), (-1e30, 1e30), (0.1, 0.3)]
+    ranges += [tuple(sorted(rng.normal(0, 10 ** rng.uniform(-3, 3), 2))) for _ in range(40)]
+    for lo, hi in ranges:
+        lo_t, hi_t = T(lo), T(hi)
+        if not hi_t > lo_t:
+            continue
+        a, b = C.c_double(), C.c_double()
+        L.check(L.lib().exenv_trunc_thresholds(L.F64 if T == np.float64 else L.F32, float(lo_t), float(hi_t),
+                                               C.byref(a), C.byref(b)))
+        lo_last, hi_first = T(a.value), T(b.value)
+        assert float(lo_last) == a.value and float(hi_first) == b.value
+        pts = [lo_t, hi_t, T(0), -T(0), T(np.inf), -T(np.inf), T(np.nan)]
+        for c in (lo_last, hi_first, lo_t, hi_t):
+            x = c
+            for _ in range(4):
+                x = np.nextafter(x, T(np.inf))
+                pts.append(x)
+            x = c
+            for _ in range(4):
+                x = np.nextafter(x, -T(np.inf))
+                pts.append(x)
+            pts.append(c)
+        x = np.concatenate([np.array(pts, T), rng.uniform(2 * lo - hi, 2 * hi - lo, 2000).astype(T)])
+        with np.errstate(invalid="ignore", over="ignore"):
+            ref = np.abs(T(2) * (x - lo_t) / (hi_t - lo_t) - T(1)) > T(1)
+        got = (x >= hi_first) | (x <= lo_last)
+        assert np.array_equal(ref, got), (lo, hi, x[ref != got][:4])
+    a, b = C.c_double(), C.c_double()
+    assert L.lib().exenv_trunc_thresholds(L.F32, 1.0, 1.0, C.byref(a), C.byref(b)) == -1
+    assert L.lib().exenv_trunc_thresholds(L.F32, 2.0, 1.0, C.byref(a), C.byref(b)) == -1

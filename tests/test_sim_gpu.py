@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from gpu_helpers import make_env, np_, to_state
-from helpers import ENVS, field_scales, random_state, traj_err
+from helpers import ENVS, field_scales, flags_from_states, random_state, traj_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -98,13 +98,25 @@ def test_sim_ahead_matches_oracle(excenvs, env, solver, dtype, layout, epilogue)
             assert err <= max(tol, 1e-5 if dtype == np.float32 else 1e-10) * 10, ("k_last", n, err)
     if not epilogue:
         return
-    # flags: bit exact wherever the oracle's observation is not within rounding distance of the threshold
-    tr_ref, tr = ref["truncated"], np_(trunc).astype(np.uint8)
-    if orc.n_trunc == orc.O:
-        safe = np.abs(np.abs(ref["obs"]) - 1.0) > max(1e-3, 100 * tol)
-        assert np.array_equal(tr[safe], tr_ref[safe])
+    # flags: bit exact -- the reference expression (IEEE NumPy, helpers.flags_from_states) applied to the states this very
+    # call returned, every environment, every saved sample; terminated as the reference defines it from them
+    tr = np_(trunc).astype(np.uint8)
+    own = [np_(getattr(states.physical_state, n)) for n in e.PHYS_FIELDS]
+    tr_def = flags_from_states(orc, own)
+    assert tr.shape == tr_def.shape and np.array_equal(tr, tr_def), (int(np.sum(tr != tr_def)), tr.size)
+    te = np_(term)[..., 0].astype(np.uint8)
+    if orc.env == "pmsm":
+        assert np.array_equal(te, tr[:, 1:, 0])  # pmsm_env.py:981-983
+    elif orc.env == "fluid_tank":
+        assert not te.any()  # fluid_tank_env.py:328-331
     else:
-        assert np.mean(tr == tr_ref) > 0.999
+        assert np.array_equal(te, (np_(rew)[..., 0] == 0).astype(np.uint8))  # reward == 0 (pendulum_env.py:387-390)
+    # and against the oracle's own flags: they can only differ where the oracle's state sits within the trajectory
+    # error of the threshold (the two state trajectories differ by rounding)
+    tr_ref = ref["truncated"]
+    if orc.n_trunc == orc.O:
+        diff = tr != tr_ref
+        assert not np.any(diff & (np.abs(np.abs(ref["obs"]) - 1.0) > 100 * tol))
     assert np.array_equal(np_(rew)[..., 0], ref["reward"])
     assert rew.shape == (B, T, 1) and term.shape == (B, T, 1) and trunc.shape == (B, T + 1, orc.n_trunc)
 
@@ -184,6 +196,10 @@ def test_reference_tracking_per_env_params_and_epilogue(excenvs, layout):
     assert _cmp(np_(obs), ref["obs"], 1e-4)
     assert _cmp(np_(rew)[..., 0], ref["reward"], 1e-3)
     assert np.mean(np_(term)[..., 0].astype(np.uint8) == ref["terminated"]) == 1.0
+    # truncated incl. the reference entries: the reference expression on the returned states, bit for bit
+    own = [np_(getattr(states.physical_state, n)) for n in e.PHYS_FIELDS]
+    assert np.array_equal(np_(trunc).astype(np.uint8), flags_from_states(orc, own, refl))
+    assert np.array_equal(np_(term)[..., 0], np_(rew)[..., 0] == 0)
 
 
 def test_max_steps_mirrors_diffrax(excenvs):
@@ -351,12 +367,14 @@ def test_time_major_envs_per_thread_and_fallbacks(excenvs, env, solver):
                 assert same(getattr(base[1].physical_state, name), getattr(other[1].physical_state, name), sc)
                 assert same(getattr(base[2].physical_state, name), getattr(other[2].physical_state, name), sc)
         bm = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau)
-        clear = (bm[0].abs() - 1).abs() > 1e-4  # flags away from the threshold cannot depend on the last bit
         for v in (0, 1, 2, 4):  # fused-epilogue flavour of every width (v = 0: the automatic choice)
             full = e.vmap_sim_ahead_with_epilogue(to_state(e, st), acts, orc.tau, orc.tau, layout="time_major",
                                                   block_envs=v)
             assert same(base[0], full[0]), (B, v)
-            assert torch.equal(full[4][clear], bm[4][clear]) and torch.equal(full[5], bm[5]), (B, v)
+            # flags: the reference expression on the states this flavour returned, bit for bit
+            own = [np_(getattr(full[1].physical_state, n)) for n in e.PHYS_FIELDS]
+            assert np.array_equal(np_(full[4]).astype(np.uint8), flags_from_states(orc, own)), (B, v)
+            assert torch.equal(full[5], bm[5]), (B, v)
             assert torch.equal(full[3], bm[3]), (B, v)
             assert full[3].shape == (B, T, 1) and full[4].shape == (B, T + 1, orc.n_trunc) and full[5].shape == (B, T, 1)
 
@@ -423,9 +441,8 @@ def test_config4_pmsm_saturated_full_horizon_properties(excenvs):
         full, c1 = getattr(st_full.physical_state, name), getattr(st1.physical_state, name)
         assert ((full[:, : T // 2] - c1[:, :-1]).abs().max() / scales[name]).item() < 1e-3, name
     # epilogue definition on the returned observations (entries 0, 1 = normalised i_d, i_q)
-    radius = torch.sqrt(o_full[..., 0] ** 2 + o_full[..., 1] ** 2)
-    clear = (radius - 1).abs() > 1e-4
-    assert torch.equal(trunc[..., 0][clear], (radius > 1)[clear])
+    own = [np_(getattr(st_full.physical_state, n)) if n in ("i_d", "i_q") else None for n in e.PHYS_FIELDS]
+    assert np.array_equal(np_(trunc).astype(np.uint8), flags_from_states(orc, own))  # bit exact, every sample
     assert torch.equal(term, trunc[:, 1:]) and bool((rew == 0).all())
     # reference-contiguous layout: same values (separate compilation: to rounding)
     o_bm, st_bm, _ = e.vmap_sim_ahead(s0, acts, e.tau, e.tau)

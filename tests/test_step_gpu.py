@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from gpu_helpers import make_env, np_, to_state
-from helpers import ENVS, field_scales, golden_oracle, random_state, scaled_err
+from helpers import ENVS, field_scales, flags_from_states, golden_oracle, random_state, scaled_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -62,10 +62,12 @@ def test_step_matches_oracle(excenvs, env, solver, dtype):
         for a, b, s_ in zip(new.additions.solver_state, ref["k"], ode_scale):
             err = scaled_err(np_(a) * orc.tau, np.asarray(b, np.float64) * orc.tau, s_)
             assert err <= TOL[dtype] * 10, ("k", err)
-    # flags are bit-exact
+    # flags are bit-exact: against the oracle and against the reference expression (IEEE NumPy) on the returned state
     assert np.array_equal(np_(trunc).astype(np.uint8), ref["truncated"])
     assert np.array_equal(np_(term)[:, 0].astype(np.uint8), ref["terminated"])
     assert np.array_equal(np_(rew)[:, 0], ref["reward"])
+    own = [np_(getattr(new.physical_state, n)) for n in e.PHYS_FIELDS]
+    assert np.array_equal(np_(trunc).astype(np.uint8), flags_from_states(orc, own))
     assert bool(new.additions.active_solver_state.all())
 
 
@@ -100,6 +102,8 @@ def test_step_with_reference_tracking_and_per_env_parameters(excenvs, env, dtype
     assert err <= TOL[dtype] * 10, ("reward", err)
     assert np.array_equal(np_(trunc).astype(np.uint8), ref["truncated"])
     assert np.array_equal(np_(term)[:, 0].astype(np.uint8), ref["terminated"])
+    own = [np_(getattr(new.physical_state, n)) for n in e.PHYS_FIELDS]
+    assert np.array_equal(np_(trunc).astype(np.uint8), flags_from_states(orc, own, ref_leaves))
 
 
 def test_inplace_step_equals_out_of_place(excenvs):
