@@ -46,6 +46,7 @@ def parse_args():
     p.add_argument("--no-other-layout", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extra", action="store_true", help="skip the extra.configs block (the other BASELINE workloads)")
     return p.parse_args()
 
 
@@ -217,6 +218,159 @@ def ncu_facts(layout):
         return {}
 
 
+# ---- the other BASELINE.json workloads, timed in the same run (extra.configs) ---------------------------------------------
+def fma_peaks(dev_index):
+    """Measured FFMA / FFMA2 / DFMA and issue-slot peaks of this GPU (tools/microbench/fma_peak.cu, built by
+    __graft_entry__.build(); a 0.1 s run).  None when the binary is missing."""
+    exe = ROOT / "tools" / "microbench" / "_build" / "fma_peak"
+    try:
+        out = subprocess.run([str(exe), str(dev_index)], capture_output=True, text=True, timeout=60).stdout
+        return json.loads(out.strip().splitlines()[-1])
+    except Exception as exc:
+        return {"error": str(exc)[:120]}
+
+
+def kernel_facts():
+    """Per-kernel constants read off the committed ncu summaries (profiles/kernel_facts.json): warp instructions and
+    FMA-pipe instructions per env-step -- the numerators of the issue / FMA rooflines of the instruction-bound kernels."""
+    try:
+        return json.load(open(ROOT / "profiles" / "kernel_facts.json"))
+    except Exception:
+        return {}
+
+
+def run_extras(ex, torch, dist, dev, rank, world, peaks):
+    """Each entry: one BASELINE workload other than the headline, device-resident, CUDA events, max over ranks."""
+    import math
+
+    hbm_peak = measured_peak_gbs()[0]
+    facts = kernel_facts()
+    f32 = torch.float32
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ex.launch_count()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n, (ex.launch_count() - l0) // n
+
+    def entry(name, workload, env_steps_per_pass, sec, launches, bytes_per_env_step, kernel, fact_key=None, dtype="f32"):
+        rate = env_steps_per_pass / sec
+        hbm = bytes_per_env_step * rate / 1e9
+        roof = {"bound": "hbm", "achieved": hbm, "peak": hbm_peak, "unit": "GB/s", "frac": hbm / hbm_peak,
+                "algorithmic_bytes_per_env_step": bytes_per_env_step}
+        f = facts.get(fact_key or "", {})
+        issue_peak = (peaks or {}).get("issue_ginst")
+        if f.get("warp_instructions_per_env_step") and issue_peak:
+            # warp instructions per second = (instructions per env-step) x (env-steps/s) / 32 lanes
+            ginst = f["warp_instructions_per_env_step"] * rate / 32 / 1e9
+            issue = {"bound": "issue", "achieved": ginst, "peak": issue_peak, "unit": "G warp-instructions/s",
+                     "frac": ginst / issue_peak, "warp_instructions_per_env_step": f["warp_instructions_per_env_step"],
+                     "ncu_source": f.get("source")}
+            if issue["frac"] > roof["frac"]:  # quote the roofline that binds, keep the other one beside it
+                roof, issue = issue, roof
+            roof["other"] = {k: issue[k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+        return {"name": name, "workload": workload, "value": world * rate, "unit": "env-steps/s", "dtype": dtype,
+                "ms_per_pass": sec * 1e3, "launches_per_pass": int(launches), "n_gpus": world, "roofline": roof,
+                "kernel": kernel}
+
+    out = []
+
+    def step_case(name, cls, solver, B, n_steps, kernel, fact_key=None, **kw):
+        env = cls(batch_size=B, solver=solver, dtype=f32, device=dev, **kw)
+        _, state = env.vmap_reset(rng=torch.Generator(device=dev).manual_seed(7 + rank))
+        # one action tensor per control step (n_steps distinct ones: 200 x 2^22 x 4 B = 3.4 GB), states updated in place
+        acts = torch.rand((n_steps, B, env.action_dim), device=dev) * 2 - 1
+        box = {"s": state}
+
+        def one_pass():
+            st = box["s"]
+            for t in range(n_steps):
+                _, st = env.vmap_step(st, acts[t], inplace=True)
+            box["s"] = st
+
+        sec, launches = timed(one_pass, 2, warm=1)
+        D, A, O = env.physical_state_dim, env.action_dim, env.obs_dim
+        tsit = isinstance(solver, ex.Tsit5)
+        bpe = 4 * (2 * D + A + O + (env.N_ODE if tsit else 0))
+        out.append(entry(name, f"{name}: batch={B}/GPU, {n_steps} vmap_step calls, one launch each, float32", B * n_steps,
+                         sec, launches, bpe, kernel, fact_key))
+        del acts, state, box
+
+    def sim_case(name, cls, solver, B, T, kernel, fact_key=None, epilogue=False, chunks=1, dtype=f32, **kw):
+        env = cls(batch_size=B, solver=solver, dtype=dtype, device=dev, **kw)
+        env.max_steps = None if T // chunks > 4096 else 4096
+        _, state = env.vmap_reset(rng=torch.Generator(device=dev).manual_seed(11 + rank))
+        D, A, O = env.physical_state_dim, env.action_dim, env.obs_dim
+        Tc = T // chunks
+        scale = 0.02 if cls is ex.PMSM else 1.0  # voltages that keep the currents inside the flux maps
+        acts = [((torch.rand((Tc, B, A), device=dev, dtype=dtype) * 2 - 1) * scale).permute(1, 0, 2) for _ in range(chunks)]
+        outb = dict(obs=torch.empty((Tc + 1, B, O), device=dev, dtype=dtype),
+                    traj=[torch.empty((Tc + 1, B), device=dev, dtype=dtype) for _ in range(D)])
+
+        def one_pass():
+            st = state
+            for c in range(chunks):  # a chunk continues from the previous one's last_state (diffrax: max_steps = 4096)
+                r = env._sim_impl(env.env_properties, B, st, acts[c], env.tau, env.tau, out=outb, layout="time_major",
+                                  epilogue=epilogue)
+                st = r[2]
+
+        sec, launches = timed(one_pass, 3, warm=2)
+        S = 4 if dtype == f32 else 8
+        bpe = S * (A + O + D) + ((S + env.n_trunc + 1) if epilogue else 0)
+        what = "vmap_sim_ahead" + (" + fused reward/truncated/terminated" if epilogue else "")
+        ch = f" as {chunks} x {Tc}-step chunks" if chunks > 1 else ""
+        out.append(entry(name, f"{name}: batch={B}/GPU, {what}, {T} steps{ch}, time-major, "
+                               f"{'float32' if dtype == f32 else 'float64'}", B * T, sec, launches, bpe, kernel, fact_key,
+                         dtype="f32" if dtype == f32 else "f64"))
+        del acts, outb, state
+        torch.cuda.empty_cache()
+
+    def guarded(fn, *a, **kw):
+        try:
+            fn(*a, **kw)
+        except Exception as exc:  # one failing extra must not take the headline down
+            out.append({"name": a[0], "error": str(exc)[:200]})
+        torch.cuda.empty_cache()
+
+    E, T5 = ex.Euler(), ex.Tsit5()
+    # north-star target 1: pendulum, explicit Euler (>= 1e11 env-steps/s on 8 GPUs)
+    guarded(step_case, "pendulum Euler vmap_step", ex.Pendulum, E, 1 << 24, 50, "step_kernel<Pendulum<float>, Euler, VEC=4>",
+            "step_pendulum_euler_f32")
+    guarded(sim_case, "pendulum Euler vmap_sim_ahead", ex.Pendulum, E, 1 << 20, 1000,
+            "simtm_kernel<Pendulum<float>, Euler, V=4>", "simtm_pendulum_euler_f32")
+    # north-star target 2 = BASELINE configs[3]: PMSM with saturated flux maps, Tsit5, fused epilogue (>= 1e10 on 8 GPUs);
+    # 2^17 environments per GPU is the shard of the 2^20 batch on 8 GPUs, 5000 steps as two 2500-step chunks
+    guarded(sim_case, "pmsm saturated (BRUSA LUT) Tsit5 vmap_sim_ahead + epilogue", ex.PMSM, T5, 1 << 17, 5000,
+            "simtm_kernel<Pmsm<float, saturated>, Tsit5, EPI>", "simtm_pmsm_sat_tsit5_f32_epi", epilogue=True, chunks=2,
+            saturated=True, motor_variant=ex.MotorVariant.BRUSA)
+    # BASELINE configs[2]: cart-pole and acrobot, B = 2^22, 200-step horizon
+    for nm, cls in (("cart_pole", ex.CartPole), ("acrobot", ex.Acrobot)):
+        guarded(step_case, f"{nm} Euler vmap_step", cls, E, 1 << 22, 200, f"step_kernel<{cls.__name__}<float>, Euler, VEC=4>",
+                f"step_{nm}_euler_f32")
+        guarded(sim_case, f"{nm} Tsit5 vmap_sim_ahead", cls, T5, 1 << 22, 200, f"simtm_kernel<{cls.__name__}<float>, Tsit5>",
+                f"simtm_{nm}_tsit5_f32")
+    # BASELINE configs[1], the fp64 half
+    guarded(sim_case, "mass_spring_damper Tsit5 vmap_sim_ahead fp64", ex.MassSpringDamper, T5, 1 << 20, 2000,
+            "simtm_kernel<MassSpringDamper<double>, Tsit5>", "simtm_msd_tsit5_f64", dtype=torch.float64)
+    return out
+
+
 def run_b200(args):
     import torch
 
@@ -379,6 +533,15 @@ def run_b200(args):
                    "error": str(exc)[:200]}
         B = B_full
 
+    extra = None
+    if not args.no_extra:
+        peaks = fma_peaks(local_rank) if rank == 0 else None
+        if dist is not None:
+            box = [peaks]
+            dist.broadcast_object_list(box, src=0)
+            peaks = box[0]
+        extra = {"fma_peak": peaks, "configs": run_extras(ex, torch, dist, dev, rank, world, peaks)}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         facts = ncu_facts(args.layout)
@@ -399,7 +562,16 @@ def run_b200(args):
                              "note": "the Tsit5 trajectory kernel sits between the fp32 FMA pipe (7 right-hand sides + dense "
                                      "output per env-step: 97 fp32 operations as 48.5 packed instructions, pipe 62 % busy) "
                                      "and HBM (55 % of peak under ncu); see profiles/README.md"},
-                "other_layout": other}
+                "other_layout": other, "extra": extra}
+        if extra and extra.get("fma_peak") and extra["fma_peak"].get("ffma2_tflops"):
+            # the headline kernel against the fp32 FMA pipe as well: packed (FFMA2 / FMUL2 / FADD2) warp instructions per
+            # second vs the measured FFMA2 instruction rate (one FFMA2 warp instruction = 128 flop)
+            fp = facts.get("packed_fp32_instructions_per_env_step")
+            if fp:
+                ginst = fp * B * T_STEPS / launch_s / 32 / 1e9
+                peak_ginst = extra["fma_peak"]["ffma2_tflops"] * 1e12 / 128 / 1e9
+                line["roofline"]["fma"] = {"achieved": ginst, "peak": peak_ginst, "unit": "G packed warp-instructions/s",
+                                           "frac": ginst / peak_ginst, "packed_fp32_instructions_per_env_step": fp}
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline()

@@ -82,6 +82,8 @@ int launch_sim_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedu
 int launch_sim_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
+int launch_simtm_packed_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream,
+                            int envs_per_thread);
 size_t sim_smem_bytes_f32(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);
 size_t sim_smem_bytes_f64(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);
 

@@ -1,4 +1,4 @@
-// exenv_simtm_packed.inl (fp32 only; included inside namespace exenv by exenv_simtm.inl when EXENV_SIMTM_PACKED is set) -- the time-major
+// exenv_simtm_packed.inl (fp32 only; included inside namespace exenv by exenv_simtm_packed_f32.cu) -- the time-major
 // trajectory kernel with PACKED fp32 arithmetic: a thread owns V = 2 or 4 consecutive environments as V / 2 values of
 // type f32x2, so every solver operation is one FFMA2 / FMUL2 / FADD2 for two environments (exenv_math.cuh).
 //

@@ -1,0 +1,45 @@
+// exenv_simtm_packed_f32.cu -- translation unit of the packed-arithmetic (FFMA2) time-major trajectory kernels:
+// environments marked env_packable, fp32, two or four environments per thread (exenv_simtm_packed.inl).
+#include "exenv_simtm_common.cuh"
+
+namespace exenv {
+
+#include "exenv_simtm_packed.inl"
+
+template <class Env, int SOLVER, int V, bool EPI>
+static int launch_simtm_packed(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
+  const SimTmK<float> a = simtm_args<Env, float>(plan, x, sch);
+  const KParams<float> kp = make_kparams<float>(plan);
+  if (sch.win_need <= 2) return launch_simtm_packed_v<Env, SOLVER, 2, V, EPI>(a, kp, x.batch, stream);
+  if (sch.win_need <= 4) return launch_simtm_packed_v<Env, SOLVER, 4, V, EPI>(a, kp, x.batch, stream);
+  set_error("sim_ahead (time-major): a solver step needs %d consecutive actions (> 4)", sch.win_need);
+  return EXENV_ERR_UNSUPPORTED;
+}
+
+template <class Env>
+static int packed_dispatch(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t st, int v) {
+  const bool tsit = plan.desc.solver == EXENV_TSIT5, epi = x.reward != nullptr;
+#define EXENV_PK(S, V, E) return launch_simtm_packed<Env, S, V, E>(plan, x, sch, st)
+  if (tsit) {
+    if (v == 4) { if (epi) EXENV_PK(EXENV_TSIT5, 4, true); EXENV_PK(EXENV_TSIT5, 4, false); }
+    if (epi) EXENV_PK(EXENV_TSIT5, 2, true);
+    EXENV_PK(EXENV_TSIT5, 2, false);
+  }
+  if (v == 4) { if (epi) EXENV_PK(EXENV_EULER, 4, true); EXENV_PK(EXENV_EULER, 4, false); }
+  if (epi) EXENV_PK(EXENV_EULER, 2, true);
+  EXENV_PK(EXENV_EULER, 2, false);
+#undef EXENV_PK
+}
+
+// v = 2 or 4 environments per thread; the caller (exenv_simtm.inl: launch_simtm_fast) has checked alignment, that the
+// batch splits into groups of v, shared parameters and control_state == [].
+int launch_simtm_packed_f32(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream,
+                            int v) {
+  switch (plan.desc.env) {
+    case EXENV_MASS_SPRING_DAMPER: return packed_dispatch<MassSpringDamper<float>>(plan, x, sch, stream, v);
+  }
+  set_error("no packed-arithmetic trajectory kernel for env %d", plan.desc.env);
+  return EXENV_ERR_UNSUPPORTED;
+}
+
+}  // namespace exenv
