@@ -92,7 +92,7 @@ class ExenvResetArgs(C.Structure):
 SYMBOLS = [
     "exenv_abi_version", "exenv_last_error", "exenv_env_dims", "exenv_launch_count", "exenv_plan_create",
     "exenv_plan_destroy", "exenv_step", "exenv_sim_ahead_shape", "exenv_sim_ahead", "exenv_sim_ahead_host",
-    "exenv_reset_pack", "exenv_schedule_build", "exenv_epilogue", "exenv_trunc_thresholds",
+    "exenv_reset_pack", "exenv_schedule_build", "exenv_epilogue", "exenv_trunc_thresholds", "exenv_sim_ahead_prepare",
 ]
 
 
@@ -128,6 +128,8 @@ def lib():
         L.exenv_sim_ahead_host.argtypes = [C.c_void_p, C.POINTER(ExenvSimArgs), C.c_int64]
         L.exenv_sim_ahead_shape.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_int64),
                                             C.POINTER(C.c_int64)]
+        L.exenv_sim_ahead_prepare.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32,
+                                              C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.exenv_reset_pack.argtypes = [C.c_void_p, C.POINTER(ExenvResetArgs), C.c_void_p]
         L.exenv_env_dims.argtypes = [C.c_int32, C.POINTER(ExenvDims)]
         L.exenv_epilogue.argtypes = [C.c_void_p, C.POINTER(ExenvEpilogueArgs), C.c_void_p]

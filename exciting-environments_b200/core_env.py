@@ -469,8 +469,10 @@ class CoreEnvironment:
             actions = self._as(actions)
         T = actions.shape[1]
         ns, nst = C.c_int64(), C.c_int64()
-        _lib.check(_lib.lib().exenv_sim_ahead_shape(plan.handle, T, obs_stepsize, action_stepsize, C.byref(ns),
-                                                    C.byref(nst)))
+        # shape of the outputs + the schedule upload of a new call shape (so that the launch below never allocates: the
+        # first call of a shape can already be captured into a CUDA graph)
+        _lib.check(_lib.lib().exenv_sim_ahead_prepare(plan.handle, T, obs_stepsize, action_stepsize, tile_steps,
+                                                      C.byref(ns), C.byref(nst)))
         NS = ns.value
         phys_in = self._phys_leaves(init_state.physical_state, B)
         out = out or {}

@@ -33,6 +33,42 @@ void set_error(const char *fmt, ...) {
     }                                                                        \
   } while (0)
 
+// Every entry point that launches, allocates or frees runs on the plan's device and leaves the calling thread's current
+// device as it found it (the caller -- torch, XLA -- owns that state).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define EX_ON_DEVICE(plan)                                                                              \
+  DeviceGuard guard_((plan)->device);                                                                   \
+  if (guard_.err != cudaSuccess) {                                                                      \
+    set_error("cannot select CUDA device %d: %s", (plan)->device, cudaGetErrorString(guard_.err));      \
+    return EXENV_ERR_CUDA;                                                                              \
+  }
+// No C++ exception crosses the C ABI (std::vector / std::map allocations of the schedule builder can throw).
+#define EX_ABI_TRY try {
+#define EX_ABI_CATCH                                             \
+  }                                                              \
+  catch (const std::bad_alloc &) {                               \
+    set_error("out of host memory");                             \
+    return EXENV_ERR_NOMEM;                                      \
+  }                                                              \
+  catch (const std::exception &e) {                              \
+    set_error("internal error: %s", e.what());                   \
+    return EXENV_ERR_INVALID;                                    \
+  }                                                              \
+  catch (...) {                                                  \
+    set_error("internal error");                                 \
+    return EXENV_ERR_INVALID;                                    \
+  }
+
 static const ExenvDims kDims[6] = {
     /* pendulum   */ {2, 2, 1, 2, 3, 2},
     /* msd        */ {2, 2, 1, 2, 3, 2},
@@ -205,24 +241,24 @@ template <typename T>
 static int upload_records(const ExenvPlan &plan, SimSchedule &s) {
   std::vector<SaveRec<T>> recs(s.theta.size() + 1);  // + one look-ahead entry
   for (int j = 0; j < 8; ++j) recs.back().v[j] = (T)0;
-  const bool tsit = plan.desc.solver == EXENV_TSIT5;
-  for (size_t i = 0; i < s.theta.size(); ++i) {
-    for (int j = 0; j < 8; ++j) recs[i].v[j] = (T)0;
-    if (tsit)
-      tsit5_dense_weights<T>((T)s.theta[i], recs[i].v);
-    else
-      recs[i].v[0] = (T)s.theta[i];
-  }
+  make_saverecs<T>(plan.desc.solver == EXENV_TSIT5, (long)s.n_steps, s.words.data(), s.dt.data(), s.theta.data(), recs);
   std::vector<T> dt(s.dt.begin(), s.dt.end());
-  dt.push_back((T)0);  // look-ahead padding (the kernel fetches step n+1 while integrating step n)
-  std::vector<StepRec<T>> steps(dt.size());
-  for (size_t i = 0; i < steps.size(); ++i) {
-    steps[i].w = i < s.words.size() ? s.words[i] : 0;
-    steps[i].dt = dt[i];
-    steps[i].pad = (T)0;
+  dt.push_back((T)0);  // look-ahead padding (the batch-major kernel fetches step n+1 while integrating step n)
+  // time-major kernels: one record per step, padded to whole 32-step chunks plus one chunk the staging runs ahead
+  const size_t n_rec = ((size_t)s.n_steps / TM_CHUNK + 2) * TM_CHUNK;
+  std::vector<TmStep<T>> steps(n_rec);
+  memset(steps.data(), 0, steps.size() * sizeof(TmStep<T>));
+  size_t save = 0;
+  for (size_t i = 0; i < (size_t)s.n_steps; ++i) {
+    steps[i].w = s.words[i];
+    steps[i].dt = (T)s.dt[i];
+    const int ns = (int)((s.words[i] >> 46) & 15ull);
+    if (ns > 0)
+      for (int j = 0; j < 8; ++j) steps[i].wts[j] = recs[save].v[j];
+    save += (size_t)ns;
   }
-  EX_CUDA(cudaMalloc(&s.d_steprec, steps.size() * sizeof(StepRec<T>)));
-  EX_CUDA(cudaMemcpy(s.d_steprec, steps.data(), steps.size() * sizeof(StepRec<T>), cudaMemcpyHostToDevice));
+  EX_CUDA(cudaMalloc(&s.d_steprec, steps.size() * sizeof(TmStep<T>)));
+  EX_CUDA(cudaMemcpy(s.d_steprec, steps.data(), steps.size() * sizeof(TmStep<T>), cudaMemcpyHostToDevice));
   EX_CUDA(cudaMalloc(&s.d_dt, dt.size() * sizeof(T)));
   EX_CUDA(cudaMalloc(&s.d_theta, recs.size() * sizeof(SaveRec<T>)));
   EX_CUDA(cudaMemcpy(s.d_dt, dt.data(), dt.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -247,6 +283,7 @@ static void free_schedule(SimSchedule &s) {
   cudaFree(s.d_tiles);
   cudaFree(s.d_steprec);
   s.d_steprec = nullptr;
+  s.uploaded = false;
   s.d_words = nullptr;
   s.d_dt = s.d_theta = nullptr;
   s.d_tiles = nullptr;
@@ -280,8 +317,12 @@ static int auto_tile_steps(const ExenvPlan &plan, int /*E*/) {
   return 1;
 }
 
+// The schedule of a (n_actions, obs_stepsize, action_stepsize) shape is built on the host once and, for the launching
+// entry points, uploaded once (cudaMalloc + synchronous cudaMemcpy).  `stream` != NULL names the stream a launch is about
+// to use: if it is being captured into a CUDA graph the upload must have happened already (exenv_sim_ahead_prepare) --
+// nothing allocates or synchronises inside a capture.
 static int get_schedule(ExenvPlan *plan, int64_t n_actions, double obs_dt, double act_dt, int tile_steps,
-                        bool need_device, SimSchedule **out) {
+                        bool need_device, SimSchedule **out, const cudaStream_t *stream = nullptr) {
   std::lock_guard<std::mutex> lock(plan->mu);
   auto key = std::make_tuple(n_actions, obs_dt, act_dt, tile_steps);
   auto it = plan->schedules.find(key);
@@ -291,10 +332,22 @@ static int get_schedule(ExenvPlan *plan, int64_t n_actions, double obs_dt, doubl
     if (rc != EXENV_OK) return rc;
     it = plan->schedules.emplace(key, std::move(s)).first;
   }
-  if (need_device && !it->second.d_words) {
-    EX_CUDA(cudaSetDevice(plan->device));
+  if (need_device && !it->second.uploaded) {
+    if (stream) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(*stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+        set_error("exenv_sim_ahead inside a stream capture needs exenv_sim_ahead_prepare(plan, %lld, %g, %g) first "
+                  "(the time schedule of a new shape is uploaded with cudaMalloc + cudaMemcpy)",
+                  (long long)n_actions, obs_dt, act_dt);
+        return EXENV_ERR_INVALID;
+      }
+    }
     int rc = upload_schedule(*plan, it->second);
-    if (rc != EXENV_OK) return rc;
+    if (rc != EXENV_OK) {  // a half-uploaded schedule must not be launched with: release it, the next call retries
+      free_schedule(it->second);
+      return rc;
+    }
+    it->second.uploaded = true;
   }
   *out = &it->second;
   return EXENV_OK;
@@ -340,6 +393,7 @@ int exenv_env_dims(int32_t env, ExenvDims *out) {
 uint64_t exenv_launch_count(void) { return g_launch_count.load(); }
 
 int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
+  EX_ABI_TRY
   if (!desc || !out) {
     set_error("exenv_plan_create: NULL argument");
     return EXENV_ERR_NULL;
@@ -392,10 +446,10 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
       return EXENV_ERR_UNSUPPORTED;
     }
   }
-  cudaError_t ce = cudaSetDevice(device);
-  if (ce != cudaSuccess) {
+  DeviceGuard guard(device);  // restores the caller's current device on every return path
+  if (guard.err != cudaSuccess) {
     set_error("exenv_plan_create: no usable CUDA device %d (%s); this library has no CPU fallback", device,
-              cudaGetErrorString(ce));
+              cudaGetErrorString(guard.err));
     delete p;
     return EXENV_ERR_CUDA;
   }
@@ -413,9 +467,12 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
     L.ny = ny;
     L.off_gy = pad16((size_t)nx * es);
     L.off_cells = L.off_gy + pad16((size_t)ny * es);
-    L.off_wx = L.off_cells + pad16((size_t)nx * ny * 6 * es);
-    L.off_wy = L.off_wx + pad16((size_t)(nx - 1) * 2 * es);
-    L.bytes = L.off_wy + pad16((size_t)(ny - 1) * 2 * es);
+    constexpr int CS = LUT_BLOB_CELL_STRIDE;
+    L.off_wx = L.off_cells + pad16((size_t)nx * ny * CS * es);
+    L.off_wy = L.off_wx + pad16((size_t)(nx - 1) * 4 * es);
+    L.bytes = L.off_wy + pad16((size_t)(ny - 1) * 4 * es);
+    L.gx0 = desc->lut_gx[0];
+    L.gy0 = desc->lut_gy[0];
     L.inv_dx = 1.0 / (desc->lut_gx[1] - desc->lut_gx[0]);
     L.inv_dy = 1.0 / (desc->lut_gy[1] - desc->lut_gy[0]);
     std::vector<unsigned char> blob(L.bytes, 0);
@@ -433,14 +490,15 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
       bool regular = true;
       const double d0 = (g[n - 1] - g[0]) / (n - 1);
       for (int i = 0; i + 1 < n; ++i) {
+        put(off, (size_t)4 * i, g[i]);
         if (es == 8) {
           const double d = g[i + 1] - g[i];
-          put(off, (size_t)2 * i, d);
-          put(off, (size_t)2 * i + 1, 1.0 / d);
+          put(off, (size_t)4 * i + 1, d);
+          put(off, (size_t)4 * i + 2, 1.0 / d);
         } else {
           const float d = (float)g[i + 1] - (float)g[i];
-          put(off, (size_t)2 * i, d);
-          put(off, (size_t)2 * i + 1, 1.0f / d);
+          put(off, (size_t)4 * i + 1, d);
+          put(off, (size_t)4 * i + 2, 1.0f / d);
         }
         regular = regular && std::fabs(g[i] - (g[0] + i * d0)) < 0.25 * std::fabs(d0);
       }
@@ -451,7 +509,7 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
     for (int q = 0; q < 6; ++q)
       for (int i = 0; i < nx; ++i)
         for (int j = 0; j < ny; ++j)
-          put(L.off_cells, ((size_t)i * ny + j) * 6 + q, desc->lut_maps[((size_t)q * nx + i) * ny + j]);
+          put(L.off_cells, ((size_t)i * ny + j) * CS + q, desc->lut_maps[((size_t)q * nx + i) * ny + j]);
     if (cudaMalloc(&L.blob, L.bytes) != cudaSuccess ||
         cudaMemcpy(L.blob, blob.data(), L.bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("exenv_plan_create: LUT upload failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -462,13 +520,20 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
   }
   *out = p;
   return EXENV_OK;
+  EX_ABI_CATCH
 }
 
 int exenv_plan_destroy(exenv_plan_t plan) {
   if (!plan) return EXENV_OK;
-  cudaSetDevice(plan->device);
-  for (auto &kv : plan->schedules) free_schedule(kv.second);
-  if (plan->lut.blob) cudaFree(plan->lut.blob);
+  {
+    DeviceGuard guard(plan->device);  // may run from a garbage collector at any time: leave the current device alone
+    for (auto &kv : plan->schedules) free_schedule(kv.second);
+    if (plan->lut.blob) cudaFree(plan->lut.blob);
+    for (int i = 0; i < 3; ++i) {
+      if (plan->host_ws[i]) cudaFree(plan->host_ws[i]);
+      if (plan->host_stream[i]) cudaStreamDestroy(plan->host_stream[i]);
+    }
+  }
   delete plan;
   return EXENV_OK;
 }
@@ -478,6 +543,7 @@ int exenv_step(exenv_plan_t plan, const ExenvStepArgs *a, void *stream) {
     set_error("exenv_step: NULL plan/args");
     return EXENV_ERR_NULL;
   }
+  EX_ON_DEVICE(plan)
   if (a->batch < 0) {
     set_error("exenv_step: negative batch");
     return EXENV_ERR_INVALID;
@@ -514,6 +580,7 @@ int exenv_reset_pack(exenv_plan_t plan, const ExenvResetArgs *a, void *stream) {
     set_error("exenv_reset_pack: NULL plan/args");
     return EXENV_ERR_NULL;
   }
+  EX_ON_DEVICE(plan)
   if (a->batch < 0 || a->mode < 0 || a->mode > 3) {
     set_error("exenv_reset_pack: bad batch/mode");
     return EXENV_ERR_INVALID;
@@ -536,6 +603,7 @@ int exenv_epilogue(exenv_plan_t plan, const ExenvEpilogueArgs *a, void *stream) 
     set_error("exenv_epilogue: NULL plan/args");
     return EXENV_ERR_NULL;
   }
+  EX_ON_DEVICE(plan)
   if (a->batch < 0) {
     set_error("exenv_epilogue: negative batch");
     return EXENV_ERR_INVALID;
@@ -561,6 +629,7 @@ int exenv_sim_ahead_shape(exenv_plan_t plan, int64_t n_actions, double obs_steps
     set_error("exenv_sim_ahead_shape: NULL plan");
     return EXENV_ERR_NULL;
   }
+  EX_ABI_TRY
   SimSchedule *s = nullptr;
   const int E = 128;
   int rc = get_schedule(plan, n_actions, obs_stepsize, action_stepsize, auto_tile_steps(*plan, E), false, &s);
@@ -568,6 +637,25 @@ int exenv_sim_ahead_shape(exenv_plan_t plan, int64_t n_actions, double obs_steps
   if (n_save) *n_save = s->n_save;
   if (n_steps) *n_steps = s->n_steps;
   return EXENV_OK;
+  EX_ABI_CATCH
+}
+
+int exenv_sim_ahead_prepare(exenv_plan_t plan, int64_t n_actions, double obs_stepsize, double action_stepsize,
+                            int32_t tile_steps, int64_t *n_save, int64_t *n_steps) {
+  if (!plan) {
+    set_error("exenv_sim_ahead_prepare: NULL plan");
+    return EXENV_ERR_NULL;
+  }
+  EX_ABI_TRY
+  EX_ON_DEVICE(plan)
+  SimSchedule *s = nullptr;
+  const int K = tile_steps > 0 ? tile_steps : auto_tile_steps(*plan, 128);
+  int rc = get_schedule(plan, n_actions, obs_stepsize, action_stepsize, K, true, &s);
+  if (rc != EXENV_OK) return rc;
+  if (n_save) *n_save = s->n_save;
+  if (n_steps) *n_steps = s->n_steps;
+  return EXENV_OK;
+  EX_ABI_CATCH
 }
 
 int exenv_schedule_build(const ExenvDesc *desc, int64_t n_actions, double obs_stepsize, double action_stepsize,
@@ -577,6 +665,7 @@ int exenv_schedule_build(const ExenvDesc *desc, int64_t n_actions, double obs_st
     set_error("exenv_schedule_build: NULL argument");
     return EXENV_ERR_NULL;
   }
+  EX_ABI_TRY
   ExenvPlan tmp;
   tmp.desc = *desc;
   tmp.deadtime = desc->env == EXENV_PMSM ? (int)desc->p[6] : 0;
@@ -594,6 +683,7 @@ int exenv_schedule_build(const ExenvDesc *desc, int64_t n_actions, double obs_st
   if (theta) memcpy(theta, s.theta.data(), s.theta.size() * sizeof(double));
   if (tiles) memcpy(tiles, s.tiles.data(), s.tiles.size() * sizeof(SimTile));
   return EXENV_OK;
+  EX_ABI_CATCH
 }
 
 int exenv_trunc_thresholds(int32_t dtype, double mn, double mx, double *lo_last, double *hi_first) {
@@ -661,10 +751,10 @@ static int validate_sim(const ExenvPlan *plan, const ExenvSimArgs *a) {
   return EXENV_OK;
 }
 
-static int prepare_sim(ExenvPlan *plan, const ExenvSimArgs *a, int *E_out, SimSchedule **sch) {
+static int prepare_sim(ExenvPlan *plan, const ExenvSimArgs *a, int *E_out, SimSchedule **sch, cudaStream_t stream) {
   const int E = 128;  // environments per CTA (compile-time constant of the sim kernel)
   int K = a->tile_steps > 0 ? a->tile_steps : auto_tile_steps(*plan, E);
-  int rc = get_schedule(plan, a->n_actions, a->obs_stepsize, a->action_stepsize, K, true, sch);
+  int rc = get_schedule(plan, a->n_actions, a->obs_stepsize, a->action_stepsize, K, true, sch, &stream);
   if (rc != EXENV_OK) return rc;
   const SimSchedule &s = **sch;
   const int64_t max_steps = a->max_steps;
@@ -686,14 +776,17 @@ int exenv_sim_ahead(exenv_plan_t plan, const ExenvSimArgs *a, void *stream) {
   int rc = validate_sim(plan, a);
   if (rc != EXENV_OK) return rc;
   if (a->batch == 0) return EXENV_OK;
+  EX_ABI_TRY
+  EX_ON_DEVICE(plan)
   int E = 0;
   SimSchedule *sch = nullptr;
-  rc = prepare_sim(plan, a, &E, &sch);
+  rc = prepare_sim(plan, a, &E, &sch, (cudaStream_t)stream);
   if (rc != EXENV_OK) return rc;
   if (a->layout == EXENV_LAYOUT_TIME_MAJOR) return launch_simtm(*plan, *a, *sch, (cudaStream_t)stream);
   ExenvSimArgs b = *a;
   b.block_envs = E;
   return launch_sim(*plan, b, *sch, (cudaStream_t)stream);
+  EX_ABI_CATCH
 }
 
 // Host-buffer variant: what a caller holding CPU arrays (the reference's CPU-JAX user) pays end to end.  The batch is
@@ -707,12 +800,13 @@ int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *h, int64_t chunk
     set_error("exenv_sim_ahead_host: host buffers are batch-major (the reference's layout)");
     return EXENV_ERR_UNSUPPORTED;
   }
-  EX_CUDA(cudaSetDevice(plan->device));
+  EX_ABI_TRY
+  EX_ON_DEVICE(plan)
   const size_t es = plan->desc.dtype == EXENV_F64 ? 8 : 4;
   const int D = plan->dims.n_phys, A = plan->dims.n_act, NODE = plan->dims.n_ode;
   const int OW = plan->dims.n_obs + plan->desc.n_control, nt = plan->dims.n_trunc;
   int64_t n_save = 0, n_steps = 0;
-  rc = exenv_sim_ahead_shape(plan, h->n_actions, h->obs_stepsize, h->action_stepsize, &n_save, &n_steps);
+  rc = exenv_sim_ahead_prepare(plan, h->n_actions, h->obs_stepsize, h->action_stepsize, h->tile_steps, &n_save, &n_steps);
   if (rc != EXENV_OK) return rc;
   const int64_t T = h->n_actions;
   // bytes per environment on the device
@@ -733,20 +827,35 @@ int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *h, int64_t chunk
     chunk_envs = (int64_t)std::max<size_t>(128, (target / per_env) / 128 * 128);
   }
   chunk_envs = std::min<int64_t>(chunk_envs, h->batch);
-  const size_t ws_bytes = per_env * (size_t)chunk_envs + (64 << 10);
-  void *ws[NSTREAM] = {nullptr, nullptr, nullptr};
-  cudaStream_t st[NSTREAM];
-  int n_st = (int)std::min<int64_t>(NSTREAM, (h->batch + chunk_envs - 1) / chunk_envs);
-  for (int i = 0; i < n_st; ++i) {
-    EX_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-    EX_CUDA(cudaMalloc(&ws[i], ws_bytes));
+  // every sub-buffer starts on a 256-byte boundary: at most 8 + 3 * D + NODE of them
+  const size_t ws_bytes = per_env * (size_t)chunk_envs + (size_t)256 * (size_t)(12 + 3 * D + NODE);
+  // The three streams and their workspaces live in the plan: created on the first call, grown when a later call needs
+  // more, released by exenv_plan_destroy.  One host-buffer call at a time per plan.
+  std::lock_guard<std::mutex> pipe_lock(plan->host_mu);
+  for (int i = 0; i < NSTREAM; ++i)
+    if (!plan->host_stream[i]) EX_CUDA(cudaStreamCreateWithFlags(&plan->host_stream[i], cudaStreamNonBlocking));
+  if (plan->host_ws_bytes < ws_bytes) {
+    for (int i = 0; i < NSTREAM; ++i) {
+      if (plan->host_ws[i]) cudaFree(plan->host_ws[i]);
+      plan->host_ws[i] = nullptr;
+    }
+    plan->host_ws_bytes = 0;
+    for (int i = 0; i < NSTREAM; ++i) EX_CUDA(cudaMalloc(&plan->host_ws[i], ws_bytes));
+    plan->host_ws_bytes = ws_bytes;
   }
+  cudaStream_t *st = plan->host_stream;
   int result = EXENV_OK;
+  cudaError_t copy_err = cudaSuccess;
+  auto copy = [&](void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s);
+    if (e != cudaSuccess && copy_err == cudaSuccess) copy_err = e;
+  };
   int slot = 0;
-  for (int64_t b0 = 0; b0 < h->batch && result == EXENV_OK; b0 += chunk_envs, slot = (slot + 1) % n_st) {
+  for (int64_t b0 = 0; b0 < h->batch && result == EXENV_OK && copy_err == cudaSuccess;
+       b0 += chunk_envs, slot = (slot + 1) % NSTREAM) {
     const int64_t nb = std::min<int64_t>(chunk_envs, h->batch - b0);
     cudaStream_t s = st[slot];
-    char *cur = (char *)ws[slot];
+    char *cur = (char *)plan->host_ws[slot];
     auto take = [&](size_t bytes) {
       char *p = cur;
       cur += (bytes + 255) & ~(size_t)255;
@@ -760,9 +869,9 @@ int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *h, int64_t chunk
       size_t bytes;
     };
     std::vector<Back> back;
-    auto in = [&](const void *host, size_t per, size_t off_elems) -> const void * {
+    auto in = [&](const void *host, size_t per, size_t off_bytes) -> const void * {
       void *dv = take(per * nb);
-      cudaMemcpyAsync(dv, (const char *)host + off_elems, per * nb, cudaMemcpyHostToDevice, s);
+      copy(dv, (const char *)host + off_bytes, per * nb, cudaMemcpyHostToDevice, s);
       return dv;
     };
     auto outb = [&](void *host, size_t per) -> void * {
@@ -785,18 +894,19 @@ int exenv_sim_ahead_host(exenv_plan_t plan, const ExenvSimArgs *h, int64_t chunk
     if (h->terminated) d.terminated = (uint8_t *)outb(h->terminated, (size_t)(n_save - 1));
     result = exenv_sim_ahead(plan, &d, s);
     if (result != EXENV_OK) break;
-    for (const Back &bk : back) cudaMemcpyAsync(bk.host, bk.dev, bk.bytes, cudaMemcpyDeviceToHost, s);
+    for (const Back &bk : back) copy(bk.host, bk.dev, bk.bytes, cudaMemcpyDeviceToHost, s);
   }
-  for (int i = 0; i < n_st; ++i) {
-    cudaError_t e = cudaStreamSynchronize(st[i]);
-    if (e != cudaSuccess && result == EXENV_OK) {
-      set_error("exenv_sim_ahead_host: %s", cudaGetErrorString(e));
-      result = EXENV_ERR_CUDA;
-    }
-    cudaFree(ws[i]);
-    cudaStreamDestroy(st[i]);
+  // one exit path: the streams are drained whatever happened above (the workspaces stay with the plan)
+  for (int i = 0; i < NSTREAM; ++i) {
+    const cudaError_t e = cudaStreamSynchronize(st[i]);
+    if (e != cudaSuccess && copy_err == cudaSuccess) copy_err = e;
+  }
+  if (result == EXENV_OK && copy_err != cudaSuccess) {
+    set_error("exenv_sim_ahead_host: %s", cudaGetErrorString(copy_err));
+    result = EXENV_ERR_CUDA;
   }
   return result;
+  EX_ABI_CATCH
 }
 
 }  // extern "C"

@@ -22,11 +22,14 @@ struct LutView {
   const T *cells;
   int nx, ny;
   T inv_dx, inv_dy;  // 1 / grid spacing: only used for the initial cell guess
-  // optional (NULL: plain IEEE division): per grid cell {width d = g[i+1] - g[i], RN(1 / d)} for the correctly rounded
-  // reciprocal division of exenv_math.cuh
+  T gx0, gy0;        // g[0] of both grids (kernel-argument copies: no read for the arithmetic cell index)
+  // optional (NULL: plain IEEE division): per grid cell four values {g[i], width d = g[i+1] - g[i], RN(1 / d), 0} -- the
+  // cell origin and the operands of the correctly rounded reciprocal division of exenv_math.cuh in one 16-byte read
   const T *wx;
   const T *wy;
   int regular;  // both grids are equidistant up to rounding: the initial guess is at most one cell off
+  int cs;       // words per grid node in `cells` (>= 6).  The device blob uses 7: with an even stride the 32 lanes of a
+                // warp, each in its own random cell, would reach only 16 of the 32 shared-memory banks per read
 };
 
 // Where the sections of the device blob prepared at plan creation live (exenv_api.cu), for building a LutView over
@@ -35,8 +38,9 @@ template <typename T>
 struct LutGeom {
   unsigned bytes, off_gy, off_cells, off_wx, off_wy;
   int nx, ny, regular;
-  T inv_dx, inv_dy;
+  T inv_dx, inv_dy, gx0, gy0;
 };
+constexpr int LUT_BLOB_CELL_STRIDE = 7;
 template <typename T>
 EX_HD LutView<T> lut_view_at(const void *base, const LutGeom<T> &g) {
   const char *b = (const char *)base;
@@ -51,6 +55,9 @@ EX_HD LutView<T> lut_view_at(const void *base, const LutGeom<T> &g) {
   L.regular = g.regular;
   L.inv_dx = g.inv_dx;
   L.inv_dy = g.inv_dy;
+  L.gx0 = g.gx0;
+  L.gy0 = g.gy0;
+  L.cs = LUT_BLOB_CELL_STRIDE;
   return L;
 }
 
@@ -76,12 +83,12 @@ EX_HD void lut_eval(const LutView<T> &L, T id, T iq, T *out) {
   T yi, yj;
   if (L.wx) {
     InvDiv<T> di, dj;
-    di.d = L.wx[2 * i];
-    di.r = L.wx[2 * i + 1];
-    dj.d = L.wy[2 * j];
-    dj.r = L.wy[2 * j + 1];
-    yi = div_inv<true, T>(id - L.gx[i], di);
-    yj = div_inv<true, T>(iq - L.gy[j], dj);
+    di.d = L.wx[4 * i + 1];
+    di.r = L.wx[4 * i + 2];
+    dj.d = L.wy[4 * j + 1];
+    dj.r = L.wy[4 * j + 2];
+    yi = div_inv<true, T>(id - L.wx[4 * i], di);
+    yj = div_inv<true, T>(iq - L.wy[4 * j], dj);
   } else {
     yi = (id - L.gx[i]) / (L.gx[i + 1] - L.gx[i]);
     yj = (iq - L.gy[j]) / (L.gy[j + 1] - L.gy[j]);
@@ -90,16 +97,92 @@ EX_HD void lut_eval(const LutView<T> &L, T id, T iq, T *out) {
   const T w01 = ((T)1 - yi) * yj;
   const T w10 = yi * ((T)1 - yj);
   const T w11 = yi * yj;
-  const T *c00 = L.cells + ((long)i * L.ny + j) * 6;
-  const T *c10 = c00 + (long)L.ny * 6;
+  const T *c00 = L.cells + ((long)i * L.ny + j) * L.cs;
+  const T *c10 = c00 + (long)L.ny * L.cs;
 #pragma unroll
   for (int q = 0; q < COUNT; ++q) {
     T v = c00[FIRST + q] * w00;
-    v += c00[6 + FIRST + q] * w01;
+    v += c00[L.cs + FIRST + q] * w01;
     v += c10[FIRST + q] * w10;
-    v += c10[6 + FIRST + q] * w11;
+    v += c10[L.cs + FIRST + q] * w11;
     out[q] = v;
   }
+}
+
+// The cell of x on an equidistant grid by arithmetic alone (no reads of the grid): floor((x - g0) / d) clipped to
+// [0, n - 2].  At a grid node (and within rounding distance of one) this may name the cell on the other side than
+// searchsorted(side="left") - 1 does; the interpolant is continuous there, so its value is the same up to rounding.
+template <typename T>
+EX_HD int lut_cell_regular(T g0, T inv_d, int n, T x) {
+  const T gf = (x - g0) * inv_d;
+  return (gf > (T)0) ? ((gf < (T)(n - 2)) ? (int)gf : n - 2) : 0;  // NaN -> 0
+}
+
+// The flux-map cell an environment's currents were last found in, as the bilinear coefficients of the six maps on that
+// cell: value_q(s, t) = a_q + bx_q s + (by_q + cxy_q s) t with s, t the offsets into the cell in units of its widths
+// (the four-corner form sum_corners c * w of RegularGridInterpolator expanded once per cell; 3 FMAs per map instead of
+// 4 products + the weights, and -- the point -- no shared-memory traffic while the currents stay in the cell: the
+// 24 corner reads per look-up with random cells per lane were the kernel's bottleneck, profiles/README.md).
+// (slo, shi] x (tlo, thi] is the set of offsets for which searchsorted(side="left") - 1, clipped to [0, n - 2], picks
+// this very cell: (0, 1] in the interior, open-ended at the map edges (linear extrapolation).  A look-up outside it
+// refills the cache through lut_cell (exact index semantics); offsets within rounding distance of a cell boundary may
+// use the neighbouring cell, where the interpolant has the same value up to rounding (it is continuous).
+template <typename T>
+struct LutCellCache {
+  T a[6], bx[6], by[6], cxy[6];
+  T x0 = (T)0, rx = (T)0, y0 = (T)0, ry = (T)0;
+  T slo = (T)0, shi = (T)-1, tlo = (T)0, thi = (T)-1;  // empty: the first look-up refills
+};
+
+template <typename T>
+EX_HD void lut_cell_refill(const LutView<T> &L, LutCellCache<T> &c, T id, T iq) {
+  int i, j;
+  if (L.wx && L.regular) {  // device blob, equidistant grids: index by arithmetic, origin + reciprocal width in one read
+    i = lut_cell_regular<T>(L.gx0, L.inv_dx, L.nx, id);
+    j = lut_cell_regular<T>(L.gy0, L.inv_dy, L.ny, iq);
+  } else {
+    i = lut_cell<T>(L.gx, L.nx, L.inv_dx, id, L.regular);
+    j = lut_cell<T>(L.gy, L.ny, L.inv_dy, iq, L.regular);
+  }
+  if (L.wx) {
+    c.x0 = L.wx[4 * i];
+    c.rx = L.wx[4 * i + 2];
+    c.y0 = L.wy[4 * j];
+    c.ry = L.wy[4 * j + 2];
+  } else {
+    c.x0 = L.gx[i];
+    c.y0 = L.gy[j];
+    c.rx = (T)1 / (L.gx[i + 1] - L.gx[i]);
+    c.ry = (T)1 / (L.gy[j + 1] - L.gy[j]);
+  }
+  const T inf = (T)INFINITY;
+  c.slo = i == 0 ? -inf : (T)0;
+  c.shi = i == L.nx - 2 ? inf : (T)1;
+  c.tlo = j == 0 ? -inf : (T)0;
+  c.thi = j == L.ny - 2 ? inf : (T)1;
+  const T *c00 = L.cells + (i * L.ny + j) * L.cs;
+  const T *c10 = c00 + L.ny * L.cs;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const T v00 = c00[q], v01 = c00[L.cs + q], v10 = c10[q], v11 = c10[L.cs + q];
+    c.a[q] = v00;
+    c.bx[q] = v10 - v00;
+    c.by[q] = v01 - v00;
+    c.cxy[q] = (v11 - v10) - (v01 - v00);
+  }
+}
+
+template <typename T, int FIRST, int COUNT>
+EX_HD void lut_eval_cached(const LutView<T> &L, LutCellCache<T> &c, T id, T iq, T *out) {
+  T s = (id - c.x0) * c.rx, t = (iq - c.y0) * c.ry;
+  if (!(s > c.slo && s <= c.shi && t > c.tlo && t <= c.thi)) {
+    lut_cell_refill<T>(L, c, id, iq);
+    s = (id - c.x0) * c.rx;
+    t = (iq - c.y0) * c.ry;
+  }
+#pragma unroll
+  for (int q = 0; q < COUNT; ++q)
+    out[q] = fma_(t, fma_(s, c.cxy[FIRST + q], c.by[FIRST + q]), fma_(s, c.bx[FIRST + q], c.a[FIRST + q]));
 }
 
 struct NoAux {};
@@ -109,6 +192,7 @@ struct PmsmAux {
   T omega_el;  // constant over a step / a sim_ahead call (pmsm_env.py:546, 639)
   int deadtime;
   LutView<T> lut;
+  mutable LutCellCache<T> cell;  // saturated maps: the cell of the last look-up (FAST paths)
 };
 
 // ---- Pendulum (pendulum/pendulum_env.py) -------------------------------------------------------------------
@@ -386,6 +470,26 @@ struct Pmsm {
       const T l_d = p[2], l_q = p[3], psi_p = p[4];
       dy[0] = div_inv<FAST, T>(u[0] + w * l_q * iq - r_s * id, q_.ld);
       dy[1] = div_inv<FAST, T>(u[1] - w * (l_d * id + psi_p) - r_s * iq, q_.lq);
+    } else if constexpr (FAST && sizeof(T) == 4) {  // :487-507 nonlinear_ode, instruction-bound fp32 kernels (fp64 keeps
+                                                    // the reference's order of operations: its per-step tolerance is 1e-12)
+      // Look-up through the cell cache; then, instead of forming inv(L) (LU with partial pivoting + two solves) and three
+      // matrix-vector products, ONE right-hand side b = -r_s i + u - omega J Psi is eliminated with the same pivoting
+      // (inv(L) b = inv(L) (-r_s i) + inv(L) u + (-inv(L) J Psi) omega up to rounding), its two divisions by pivots as
+      // Newton-refined reciprocals (exenv_math.cuh: rcp_nr, ~1 ulp).  The differential inductances are well conditioned
+      // (L_dd, L_qq dominate by >10x): the derivative moves by a few ulp, far inside the per-step tolerance.
+      T q[6];
+      lut_eval_cached<T, 0, 6>(aux.lut, aux.cell, id, iq, q);
+      const T rhs0 = fma_(w, q[5], fma_(-r_s, id, u[0]));   // u_d - r_s i_d + omega Psi_q
+      const T rhs1 = fma_(-w, q[4], fma_(-r_s, iq, u[1]));  // u_q - r_s i_q - omega Psi_d
+      const bool swap = Mth<T>::abs(q[2]) > Mth<T>::abs(q[0]);
+      const T b00 = swap ? q[2] : q[0], b01 = swap ? q[3] : q[1];
+      const T b10 = swap ? q[0] : q[2], b11 = swap ? q[1] : q[3];
+      const T r0 = swap ? rhs1 : rhs0, r1 = swap ? rhs0 : rhs1;
+      const T i00 = rcp_nr(b00);
+      const T lf = b10 * i00;
+      const T x1 = fma_(-lf, r0, r1) * rcp_nr(fma_(-lf, b01, b11));
+      dy[0] = fma_(-b01, x1, r0) * i00;
+      dy[1] = x1;
     } else {  // :487-507 nonlinear_ode
       T q[6];
       lut_eval<T, 0, 6>(aux.lut, id, iq, q);
@@ -420,12 +524,14 @@ struct Pmsm {
   EX_HD static bool is_angle(int) { return false; }
 
   // :365-381 currents_to_torque / currents_to_torque_saturated
+  template <bool FAST = false>
   EX_HD static T torque(T id, T iq, const T *p, const Aux &aux) {
     if constexpr (!SAT) {
       return (T)1.5 * p[0] * (p[4] + (p[2] - p[3]) * id) * iq;
     } else {
       T q[2];
-      lut_eval<T, 4, 2>(aux.lut, id, iq, q);
+      if constexpr (FAST && sizeof(T) == 4) lut_eval_cached<T, 4, 2>(aux.lut, aux.cell, id, iq, q);  // usually a hit
+      else lut_eval<T, 4, 2>(aux.lut, id, iq, q);
       return (T)1.5 * p[0] * (q[0] * iq - q[1] * id);
     }
   }

@@ -33,12 +33,13 @@ struct SimSchedule {
   int64_t n_actions = 0, n_save = 0, n_steps = 0;
   int tile_steps = 0, n_tiles = 0, act_cap = 0, save_cap = 0;
   int win_need = 1;  // time-major kernel: consecutive staged action indices a single solver step reads (from its base)
+  bool uploaded = false;  // every device copy below is complete
   // device copies
   uint64_t *d_words = nullptr;  // bits 0-31 min action index, 32-45 seven 2-bit stage deltas, 46-49 #saves
   void *d_dt = nullptr;         // T[n_steps]   tnext - tprev
   void *d_theta = nullptr;      // SaveRec<T>[n_save]  dense-output record of every save, in save order
   SimTile *d_tiles = nullptr;
-  void *d_steprec = nullptr;    // StepRec<T>[n_steps + 1]  packed (word, dt) for the time-major kernel
+  void *d_steprec = nullptr;    // TmStep<T>[chunks of 32, padded]: (word, dt, first-save record) per step, time-major kernels
   // host copies (tests / shape queries)
   std::vector<uint64_t> words;
   std::vector<double> dt, theta;
@@ -46,11 +47,11 @@ struct SimSchedule {
 };
 
 struct DevLut {
-  void *blob = nullptr;  // [gx | gy | cells | wx | wy] in the plan dtype, 16-byte padded sections
+  void *blob = nullptr;  // [gx | gy | cells (7 words per node) | wx | wy (4 words per cell)] in the plan dtype, 16-byte padded sections
   size_t bytes = 0, off_gy = 0, off_cells = 0, off_wx = 0, off_wy = 0;
   int nx = 0, ny = 0;
   int regular = 0;       // both grids equidistant up to rounding (cell guess at most one off)
-  double inv_dx = 0, inv_dy = 0;
+  double inv_dx = 0, inv_dy = 0, gx0 = 0, gy0 = 0;
 };
 
 }  // namespace exenv
@@ -65,6 +66,12 @@ struct ExenvPlan {
   exenv::DevLut lut;
   std::mutex mu;
   std::map<std::tuple<int64_t, double, double, int>, exenv::SimSchedule> schedules;
+  // exenv_sim_ahead_host: three copy/compute streams and their device workspaces, created on first use, kept for the
+  // life of the plan (grown when a call needs more)
+  std::mutex host_mu;
+  cudaStream_t host_stream[3] = {nullptr, nullptr, nullptr};
+  void *host_ws[3] = {nullptr, nullptr, nullptr};
+  size_t host_ws_bytes = 0;
 };
 
 namespace exenv {

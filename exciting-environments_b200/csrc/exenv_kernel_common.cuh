@@ -46,6 +46,8 @@ inline LutGeom<T> make_lut_geom(const ExenvPlan &plan) {
   g.regular = plan.lut.regular;
   g.inv_dx = (T)plan.lut.inv_dx;
   g.inv_dy = (T)plan.lut.inv_dy;
+  g.gx0 = (T)plan.lut.gx0;
+  g.gy0 = (T)plan.lut.gy0;
   return g;
 }
 template <typename T>
@@ -153,7 +155,7 @@ EX_HD void env_step_one(T *s, const T *a, const T *p, typename Env::Aux &aux, T 
     s[3] = y1[0];
     s[4] = y1[1];
     s[2] = y1[2];
-    s[5] = Env::torque(y1[0], y1[1], p, aux);
+    s[5] = Env::template torque<FD>(y1[0], y1[1], p, aux);
   } else {
 #pragma unroll
     for (int i = 0; i < NODE; ++i) s[i] = y1[i];

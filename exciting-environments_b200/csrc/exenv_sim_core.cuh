@@ -25,20 +25,46 @@ constexpr int staged_values() {
   return Env::IS_PMSM ? 8 : Env::NODE;
 }
 
-// Per-save dense-output record built by the host (exenv_api.cu): Tsit5 -> the seven weights b_i(theta) of
-// diffrax's _Tsit5Interpolation, evaluated in T exactly like tsit5_dense_weights; Euler -> v[0] = theta.
+// Per-save dense-output record built by the host (make_saverec below; exenv_api.cu, tests/hostcheck): Tsit5 -> the
+// seven weights b_i(theta) of diffrax's _Tsit5Interpolation, evaluated in T exactly like tsit5_dense_weights and
+// multiplied by the length dt of the step the save falls into (the kernels keep derivatives, not increments:
+// y(theta) = y0 + sum_i (b_i(theta) dt) f_i); Euler -> v[0] = theta.
 template <typename T>
 struct alignas(16) SaveRec {
   T v[8];
 };
-
-// Packed per-step schedule entry of the time-major kernel (one 16-byte load in fp32).
 template <typename T>
-struct alignas(16) StepRec {
+inline void make_saverec(bool tsit5, double theta, double dt_step, SaveRec<T> &r) {
+  for (int j = 0; j < 8; ++j) r.v[j] = (T)0;
+  if (tsit5) {
+    tsit5_dense_weights<T>((T)theta, r.v);
+    for (int j = 0; j < 7; ++j) r.v[j] = r.v[j] * (T)dt_step;
+  } else {
+    r.v[0] = (T)theta;
+  }
+}
+// Records of a whole schedule: save s belongs to the step that counts it in bits 46-49 of its word.
+template <typename T, class Vec>
+inline void make_saverecs(bool tsit5, long n_steps, const uint64_t *words, const double *dts, const double *thetas,
+                          Vec &recs) {
+  long s = 0;
+  for (long n = 0; n < n_steps; ++n) {
+    const int ns = (int)((words[n] >> 46) & 15ull);
+    for (int q = 0; q < ns; ++q, ++s) make_saverec<T>(tsit5, thetas[s], dts[n], recs[(size_t)s]);
+  }
+}
+
+// Per-step schedule entry of the time-major kernels: the schedule word, the step length and the dense-output record of
+// the step's FIRST save (zeros when the step saves nothing; further saves of the same step -- rare -- are read from the
+// per-save SaveRec array).  48 bytes in fp32, 96 in fp64; staged through shared memory 32 steps at a time.
+template <typename T>
+struct alignas(16) TmStep {
   uint64_t w;
   T dt;
   T pad;
+  T wts[8];
 };
+constexpr int TM_CHUNK = 32;  // steps per staged chunk (one record per lane)
 
 // Action of stage `s` of the step described by word `w`.  A fetch object may provide stage(w, s, u) and decode the
 // 2-bit stage offset itself (time-major kernel: its window starts at the step's base index); plain callables
@@ -109,13 +135,13 @@ EX_HD void sim_save_one(const SaveRec<RT> &rec, const T *y, const T *y1, const T
   if constexpr (SOLVER == EXENV_EULER) {  // LocalLinearInterpolation
 #pragma unroll
     for (int i = 0; i < NODE; ++i) ysv[i] = y[i] + rec.v[0] * (y1[i] - y[i]);
-  } else {  // _Tsit5Interpolation
+  } else {  // _Tsit5Interpolation on the stage derivatives k = f (weights carry the step length, see SaveRec)
 #pragma unroll
     for (int i = 0; i < NODE; ++i) {
-      T acc = rec.v[0] * k[0][i];
+      T acc = fma_(T(rec.v[0]), k[0][i], y[i]);
 #pragma unroll
-      for (int j = 1; j < 7; ++j) acc += rec.v[j] * k[j][i];
-      ysv[i] = y[i] + acc;
+      for (int j = 1; j < 7; ++j) acc = fma_(T(rec.v[j]), k[j][i], acc);
+      ysv[i] = acc;
     }
   }
   Env::post(ysv);
@@ -123,7 +149,7 @@ EX_HD void sim_save_one(const SaveRec<RT> &rec, const T *y, const T *y1, const T
     st[0] = ysv[2];
     st[1] = ysv[0];
     st[2] = ysv[1];
-    st[3] = Env::torque(ysv[0], ysv[1], p, aux);
+    st[3] = Env::template torque<true>(ysv[0], ysv[1], p, aux);
     // u_dq buffer leaves of saved state j: vstack([buffer]*deadtime, clipped actions)[j]; zeros when
     // deadtime == 0 (pmsm_env.py:785-791) -- the same dead-time shifted sequence the solver reads
     T ub[A];
@@ -156,18 +182,19 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
       k[0][i] = f0[i] * dt;
       y1[i] = y[i] + k[0][i];
     }
-  } else {  // diffrax.Tsit5 with FSAL
-    T fl[NODE];
-    tsit5_step<T, NODE>(
-        y, f, dt,
+  } else {  // diffrax.Tsit5 with FSAL, derivative form (exenv_math.cuh: tsit5_step_f): k holds f_1 .. f_7
+#pragma unroll
+    for (int i = 0; i < NODE; ++i) k[0][i] = f[i];
+    tsit5_step_f<T, NODE>(
+        y, dt,
         [&](int stage, const T *ys, T *fo) {
           T u[A];
           fetch_stage_(fetch, w, stage, u, 0);
           sim_rhs<Env, T>(ys, u, p, pre, aux, fo);
         },
-        y1, fl, k);
+        y1, k);
 #pragma unroll
-    for (int i = 0; i < NODE; ++i) f[i] = fl[i];
+    for (int i = 0; i < NODE; ++i) f[i] = k[6][i];
   }
   // SaveAt(ts): dense output at the scheduled abscissae; one save per step is the common case
   const int ns = sched_saves(w);

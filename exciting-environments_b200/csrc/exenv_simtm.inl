@@ -35,10 +35,16 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   static_assert(!(GENERIC && EPI), "EPI is the fused-epilogue flavour of the fast instantiation");
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
-  const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;  // first environment of this thread
-  const bool valid = b < a.B;
+  // First environment of this thread.  A warp entirely beyond the batch leaves; in the warp that straddles its end the
+  // surplus lanes shadow the last group of V environments (same loads, same arithmetic, same values stored to the same
+  // addresses): every warp that runs the loop runs it with all 32 lanes, which the shared-memory schedule staging needs.
+  const long b_own = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const bool valid = b_own - (long)(threadIdx.x & 31) * V < a.B;
+  const long b = b_own < a.B ? b_own : a.B - V;
 
   typename Env::Aux aux[V];
+  // dynamic shared memory: [PMSM flux maps + mbarrier (saturated only) | per-warp schedule buffers]
+  const unsigned sched_off = (Env::IS_PMSM && Env::SATURATED) ? ((a.lut.bytes + 16 + 15) & ~15u) : 0u;
   if constexpr (Env::IS_PMSM && Env::SATURATED) {
     // stage the flux maps once per CTA: TMA bulk copy + mbarrier (SASS: UBLKCP)
     unsigned char *sm_lut = smem_raw;
@@ -349,28 +355,33 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     }
   };
 
-  // ---- the solver loop: the packed (word, dt) entry of step i+1 is fetched while step i is integrated; the dense-
-  // output record of a step is only needed after its last stage, so its load is issued at the top of the same step
+  // ---- the solver loop: the schedule record of a step (word, step length, dense-output record of its first save)
+  // comes out of this warp's shared-memory copy (TmSchedReader); the only global load of the loop is the action stream's
   long save_idx = 0;
-  const StepRec<T> *sp = a.steps;
-  StepRec<T> s_next = load_steprec<T>(sp);
-  slide_to(sched_base(s_next.w));
-  if constexpr (SOLVER == EXENV_TSIT5) {
+  TmSchedReader<T> sched;
+  sched.init(a.steps, smem_raw + sched_off);
+  {
+    const uint64_t w0 = sched.chunk(0)->w;
+    slide_to(sched_base(w0));
+    if constexpr (SOLVER == EXENV_TSIT5) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) sim_first_derivative<Env, T>(s_next.w, y[v], f[v], p, pre, aux[v], win[v]);
+      for (int v = 0; v < V; ++v) sim_first_derivative<Env, T>(w0, y[v], f[v], p, pre, aux[v], win[v]);
+    }
   }
   const int n_steps = (int)a.n_steps;
 #pragma unroll 1
-  for (int i = 0; i < n_steps; ++i) {
-    const uint64_t w = s_next.w;
-    const T dt = s_next.dt;
-    // Load order at the top of a step: the window slide consumes the action that
-    // left for DRAM one step ago; the warp-uniform schedule entries (L1 hits) are loaded and waited for; only then
-    // is the next action load issued, so that no scoreboard wait inside the step sits behind a DRAM access.
+  for (int i0 = 0; i0 < n_steps; i0 += TM_CHUNK) {  // 32 steps per staged chunk of schedule records
+  const TmStep<T> *sr = sched.chunk(i0 / TM_CHUNK);
+  const int n_in = min(TM_CHUNK, n_steps - i0);
+#pragma unroll 1
+  for (int k = 0; k < n_in; ++k, ++sr) {
+    const uint64_t w = sr->w;
+    const T dt = sr->dt;
+    // the window slide consumes the action that left for DRAM one step ago; the next action load is issued right after
     slide_to(sched_base(w));
     SaveRec<T> rec;
-    load_saverec<SOLVER, T>(rec, a.recs + save_idx);
-    s_next = load_steprec<T>(++sp);  // one look-ahead entry is appended by the host
+#pragma unroll
+    for (int j = 0; j < (SOLVER == EXENV_EULER ? 1 : 7); ++j) rec.v[j] = sr->wts[j];
     if (!pend_valid) {
       load_next(pend);
       pend_valid = true;
@@ -396,6 +407,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     const int ns = sched_saves(w);
     if (ns > 0) flush(ns);
     save_idx = si;
+  }
   }
 
   // ---- last_state (core_env.py:484-488) and the fresh solver.init derivative at (t1, y_last) --------------------
@@ -446,7 +458,8 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   const SimTmK<T> a = simtm_args<Env, T>(plan, x, sch);
   KParams<T> kp = make_kparams<T>(plan);
   size_t smem = 0;
-  if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = plan.lut.bytes + 16;
+  if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = (plan.lut.bytes + 16 + 15) & ~(size_t)15;
+  smem += tm_sched_smem_bytes<T>(SIMTM_THREADS);
   auto kern = simtm_kernel<Env, SOLVER, T, PER_ENV, GENERIC, W, V, EPI>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

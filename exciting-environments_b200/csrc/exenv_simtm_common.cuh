@@ -42,7 +42,7 @@ struct SimTmK {
   T *reward;       // (N, B)
   uint8_t *trunc;  // (N+1, B, n_trunc)
   uint8_t *term;   // (N, B)
-  const StepRec<T> *steps;  // packed (schedule word, step length) per solver step + one look-ahead entry
+  const TmStep<T> *steps;  // per solver step: schedule word, step length, first-save record (staged through smem)
   const SaveRec<T> *recs;
   int n_control;
   int control[EXENV_MAX_CONTROL];
@@ -128,59 +128,53 @@ __device__ __forceinline__ void load_vec(T *v, const T *src) {
     ldcs_chunk<CH>(reinterpret_cast<char *>(v) + i * CH, reinterpret_cast<const char *>(src) + i * CH);
 }
 
-// Schedule entries are warp-uniform; explicit vector loads of exactly the fields the solver reads (a padded 128-bit
-// load would make the unused lane a write-after-write hazard for whatever the compiler puts there next).
+// ---- the schedule, staged through shared memory -------------------------------------------------------------------------
+// Every warp of the grid walks the same per-step records (TmStep: word, step length, first-save record).  Reading them
+// with global loads put them on the scoreboard of the action stream's DRAM load (ptxas shares one scoreboard between
+// the loads of the loop), so the first use of a record waited for DRAM, and a lane of a merged 16-byte load that the
+// step does not use made that wait a write-after-write stall at the top of the step: 22-27 % of the stall samples of
+// the headline kernel (profiles/README.md, round 2).  Each warp therefore copies the records of the next 32 steps into
+// its own shared-memory buffer with cp.async (LDGSTS: no register, no scoreboard; one record per lane, double
+// buffered, one __syncwarp per 32 steps) and reads them back with broadcast LDS.
 template <typename T>
-__device__ __forceinline__ StepRec<T> load_steprec(const StepRec<T> *p) {
-  StepRec<T> r;
-  if constexpr (sizeof(T) == 4) {  // 8 + 4 bytes: no destination register without a consumer (a 16-byte load's padding
-                                   // lane is reused at once and its write-after-write wait queues behind the action
-                                   // load: Euler trajectories +6 %, profiles/README.md)
-    uint2 q2;
-    unsigned d;
-    ld_chunk<8, true>(&q2, p);
-    ld_chunk<4, true>(&d, reinterpret_cast<const char *>(p) + 8);
-    r.w = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
-    r.dt = __uint_as_float(d);
-    consume_now(d);
-    r.pad = (T)0;
-    return r;
-  } else {
-    uint4 q;
-    ld_chunk<16, true>(&q, p);
-    r.w = (uint64_t)q.x | ((uint64_t)q.y << 32);
-    r.dt = __hiloint2double((int)q.w, (int)q.z);
-    consume_now(q.w);
-    r.pad = (T)0;
-    return r;
-  }
+constexpr size_t tm_sched_smem_bytes(int threads) {
+  return (size_t)(threads / 32) * 2 * TM_CHUNK * sizeof(TmStep<T>);
 }
-template <int SOLVER, typename T>
-__device__ __forceinline__ void load_saverec(SaveRec<T> &r, const SaveRec<T> *p) {
-  constexpr int N = SOLVER == EXENV_EULER ? 1 : 7;  // Euler: theta; Tsit5: seven dense-output weights
-  constexpr int BYTES = N * (int)sizeof(T);
-  char *dst = reinterpret_cast<char *>(r.v);
-  const char *src = reinterpret_cast<const char *>(p->v);
-  int off = 0;
+template <typename T>
+struct TmSchedReader {
+  const TmStep<T> *g;  // global records (padded to whole chunks + one, exenv_api.cu: upload_records)
+  TmStep<T> *buf;      // this warp's two chunk buffers
+  __device__ __forceinline__ void stage(int chunk) {  // lane l copies the record of step chunk * 32 + l
+    constexpr int CH16 = (int)sizeof(TmStep<T>) / 16;
+    const unsigned lane = threadIdx.x & 31u;
+    const char *src = reinterpret_cast<const char *>(g + (size_t)chunk * TM_CHUNK + lane);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (chunk & 1) * TM_CHUNK + lane);
 #pragma unroll
-  for (int ch = 16; ch >= 4; ch >>= 1) {
-#pragma unroll
-    for (int rep = 0; rep < 4; ++rep) {
-      if (off + ch <= BYTES) {
-        if (ch == 16) ld_chunk<16, true>(dst + off, src + off);
-        else if (ch == 8) ld_chunk<8, true>(dst + off, src + off);
-        else ld_chunk<4, true>(dst + off, src + off);
-        off += ch;
-      }
-    }
+    for (int c = 0; c < CH16; ++c)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c * 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  unsigned last_word;
-  memcpy(&last_word, dst + BYTES - 4, 4);
-  consume_now(last_word);
-  unsigned first_word;
-  memcpy(&first_word, dst, 4);
-  consume_now(first_word);
-}
+  // Call once, with all 32 lanes of the warp, before the first at().  (A warp that straddles the end of the batch keeps
+  // its surplus lanes: they shadow the last environment group, see the kernels.)
+  __device__ __forceinline__ void init(const TmStep<T> *records, unsigned char *smem_base) {
+    g = records;
+    buf = reinterpret_cast<TmStep<T> *>(smem_base) + (size_t)(threadIdx.x >> 5) * 2 * TM_CHUNK;
+    stage(0);
+    enter_chunk(0);
+  }
+  // chunk c has landed (it was requested 32 steps ago); request chunk c + 1 into the other buffer, whose previous
+  // content (chunk c - 1) every lane has finished reading
+  __device__ __forceinline__ void enter_chunk(int c) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    stage(c + 1);
+  }
+  // records of steps [32 c, 32 c + 32); chunks must be visited in order (chunk 0 is ready after init())
+  __device__ __forceinline__ const TmStep<T> *chunk(int c) {
+    if (c) enter_chunk(c);
+    return buf + (c & 1) * TM_CHUNK;
+  }
+};
 
 // The window of prepared actions as the `fetch` object of exenv_sim_core.cuh.  Slot 0 holds the step's base index
 // (the kernel slides the window before every step), so a stage's action is selected by its 2-bit offset alone.
@@ -310,7 +304,7 @@ static SimTmK<T> simtm_args(const ExenvPlan &plan, const ExenvSimArgs &x, const 
   a.reward = (T *)x.reward;
   a.trunc = x.truncated;
   a.term = x.terminated;
-  a.steps = (const StepRec<T> *)sch.d_steprec;
+  a.steps = (const TmStep<T> *)sch.d_steprec;
   a.recs = (const SaveRec<T> *)sch.d_theta;
   a.n_control = plan.desc.n_control;
   for (int j = 0; j < EXENV_MAX_CONTROL; ++j) a.control[j] = plan.desc.control[j];

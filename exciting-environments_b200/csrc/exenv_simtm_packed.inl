@@ -22,8 +22,11 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   constexpr int NST = staged_values<Env>(), VV = V / 2;
   constexpr int NT0 = trunc_dim<Env>(0);
 
-  const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;  // first environment of this thread
-  if (b >= a.B) return;
+  // first environment of this thread; surplus lanes of the warp that straddles the end of the batch shadow the last
+  // group of V environments (see exenv_simtm.inl)
+  const long b_own = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (b_own - (long)(threadIdx.x & 31) * V >= a.B) return;
+  const long b = b_own < a.B ? b_own : a.B - V;
 
   // shared parameters: scalars (constant bank); the packed copy is a splat the compiler folds into broadcast operands
   const T *p = kp.v;
@@ -230,24 +233,32 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
     }
   };
 
-  // ---- the solver loop (same order of loads as the scalar kernel) -----------------------------------------------
+  // ---- the solver loop (schedule records from this warp's shared-memory copy, see exenv_simtm_common.cuh) ---------
   long save_idx = 0;
-  const StepRec<T> *sp = a.steps;
-  StepRec<T> s_next = load_steprec<T>(sp);
-  slide_to(sched_base(s_next.w));
-  if constexpr (SOLVER == EXENV_TSIT5) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TmSchedReader<T> sched;
+  sched.init(a.steps, smem_raw);
+  {
+    const uint64_t w0 = sched.chunk(0)->w;
+    slide_to(sched_base(w0));
+    if constexpr (SOLVER == EXENV_TSIT5) {
 #pragma unroll
-    for (int vv = 0; vv < VV; ++vv) sim_first_derivative<EnvP, P>(s_next.w, y[vv], f[vv], pq, pre, aux, win[vv]);
+      for (int vv = 0; vv < VV; ++vv) sim_first_derivative<EnvP, P>(w0, y[vv], f[vv], pq, pre, aux, win[vv]);
+    }
   }
   const int n_steps = (int)a.n_steps;
 #pragma unroll 1
-  for (int i = 0; i < n_steps; ++i) {
-    const uint64_t w = s_next.w;
-    const P dt = P(s_next.dt);
+  for (int i0 = 0; i0 < n_steps; i0 += TM_CHUNK) {  // 32 steps per staged chunk of schedule records
+  const TmStep<T> *sr = sched.chunk(i0 / TM_CHUNK);
+  const int n_in = min(TM_CHUNK, n_steps - i0);
+#pragma unroll 1
+  for (int k = 0; k < n_in; ++k, ++sr) {
+    const uint64_t w = sr->w;
+    const P dt = P(sr->dt);
     slide_to(sched_base(w));
     SaveRec<T> rec;
-    load_saverec<SOLVER, T>(rec, a.recs + save_idx);
-    s_next = load_steprec<T>(++sp);
+#pragma unroll
+    for (int j = 0; j < (SOLVER == EXENV_EULER ? 1 : 7); ++j) rec.v[j] = sr->wts[j];
     if (!pend_valid) {
       load_next(pend);
       pend_valid = true;
@@ -273,6 +284,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
     const int ns = sched_saves(w);
     if (ns > 0) flush(ns);
     save_idx = si;
+  }
   }
 
   // ---- last_state and the fresh solver.init derivative at (t1, y_last) --------------------------------------------
@@ -335,7 +347,7 @@ static int launch_simtm_packed_v(const SimTmK<float> &a, const KParams<float> &k
     set_error("sim_ahead (time-major, packed): degenerate normalisation range for the fused truncation flags");
     return EXENV_ERR_INVALID;
   }
-  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, nthr, 0, stream>>>(a, kp, hp);
+  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, nthr, tm_sched_smem_bytes<float>(SIMTM_THREADS), stream>>>(a, kp, hp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -31,8 +31,9 @@
  *     contiguous segment.  The host mirror returns them as permuted views with the reference's shapes.
  *   - Outputs may alias the matching inputs leaf-by-leaf (each thread reads its element before writing it).
  *   - Kernels never allocate or retain caller pointers past the call; launches are asynchronous on `stream`
- *     (a cudaStream_t passed as void*), no host synchronisation, CUDA-graph capturable after the first call of a
- *     given (n_actions, obs_stepsize, action_stepsize) shape (that first call builds and uploads the time schedule).
+ *     (a cudaStream_t passed as void*), no host synchronisation, CUDA-graph capturable (exenv_sim_ahead: after
+ *     exenv_sim_ahead_prepare for the call shape; inside a capture an unprepared shape is an error, never a malloc).
+ *     Every entry point runs on the plan's device and restores the calling thread's current device.
  *   - Return value: EXENV_OK or a negative ExenvStatus; exenv_last_error() gives the thread-local message.
  *     There is NO CPU fallback: without a CUDA device every compute entry point returns EXENV_ERR_CUDA.
  */
@@ -177,6 +178,13 @@ typedef struct ExenvSimArgs {
  * emulated diffeqsolve loop in the plan dtype. */
 int exenv_sim_ahead_shape(exenv_plan_t plan, int64_t n_actions, double obs_stepsize, double action_stepsize,
                           int64_t *n_save, int64_t *n_steps);
+/* Builds and uploads the time schedule of this call shape (host work, cudaMalloc, one synchronous cudaMemcpy) ahead of
+ * time, so that exenv_sim_ahead itself only launches: required before the first exenv_sim_ahead of a shape that is issued
+ * inside a CUDA-graph capture / an XLA custom call (which must not allocate or synchronise); otherwise optional --
+ * outside a capture exenv_sim_ahead prepares lazily.  tile_steps as in ExenvSimArgs (0 = auto).  Also returns the shape
+ * like exenv_sim_ahead_shape (pointers may be NULL). */
+int exenv_sim_ahead_prepare(exenv_plan_t plan, int64_t n_actions, double obs_stepsize, double action_stepsize,
+                            int32_t tile_steps, int64_t *n_save, int64_t *n_steps);
 int exenv_sim_ahead(exenv_plan_t plan, const ExenvSimArgs *args, void *stream);
 /* Same call with HOST buffers (pinned or pageable); chunk_envs environments per pipeline stage (0 = auto).
  * Host buffers are always in the reference's batch-major layout (layout must be EXENV_LAYOUT_BATCH_MAJOR). */

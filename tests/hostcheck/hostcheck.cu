@@ -36,6 +36,7 @@ static LutView<T> view(const HcLut *l) {
     v.ny = l->ny;
     v.inv_dx = (T)l->inv_dx;
     v.inv_dy = (T)l->inv_dy;
+    v.cs = 6;
   }
   return v;
 }
@@ -67,11 +68,7 @@ static void sim_t(const ExenvDesc *d, const HcLut *lut, long B, long n_actions, 
                   const T *actions, T *const *traj /* NST leaves (B, n_save) */) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, NST = staged_values<Env>();
   std::vector<SaveRec<T>> recs((size_t)n_save);
-  for (long i = 0; i < n_save; ++i) {
-    for (int j = 0; j < 8; ++j) recs[(size_t)i].v[j] = (T)0;
-    if (SOLVER == EXENV_EULER) recs[(size_t)i].v[0] = (T)thetas[i];
-    else tsit5_dense_weights<T>((T)thetas[i], recs[(size_t)i].v);
-  }
+  make_saverecs<T>(SOLVER == EXENV_TSIT5, n_steps, words, dts, thetas, recs);
   const double dead_d = Env::IS_PMSM ? d->p[6] : 0.0;
   const int dead = (int)dead_d;
   for (long b = 0; b < B; ++b) {
