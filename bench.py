@@ -47,6 +47,9 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extra", action="store_true", help="skip the extra.configs block (the other BASELINE workloads)")
+    p.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"],
+                   help="how SM clocks / throttle reasons are sampled during the timed region: an in-process NVML thread "
+                        "(default; falls back to nvidia-smi when pynvml is missing), an `nvidia-smi -lms` child, or not at all")
     return p.parse_args()
 
 
@@ -192,6 +195,75 @@ class ClockSampler:
             out["power_w_max"] = max(pw) if pw else None
             out["window"] = window
         return out
+
+
+class NvmlClockSampler:
+    """The same samples through NVML from a thread of this process (no child process polling the driver): SM clock,
+    power and the clocks-event reasons every 20 ms with their wall-clock time stamps."""
+
+    def __init__(self, gpu_index):
+        import threading
+
+        import pynvml
+
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        import torch
+
+        pr = torch.cuda.get_device_properties(gpu_index)
+        self.h = pynvml.nvmlDeviceGetHandleByPciBusId(
+            f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        self.rows, self.stop_flag = [], False
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((time.time(), float(mhz), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self, t0=None, t1=None):
+        nv = self.nv
+        time.sleep(0.03)
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "how": "NVML thread, 20 ms"}
+        inside = [r for r in self.rows if t0 is not None and t0 - 0.01 <= r[0] <= t1 + 0.01]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for r in self.rows if t0 is None or r[0] >= t0 - 0.5] or self.rows, "nearest to the timed region"
+        if inside:
+            sm = sorted(r[1] for r in inside)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_mhz_min=sm[0], samples=len(sm), window=window,
+                       power_w_max=max(r[2] for r in inside))
+            bits = 0
+            for r in inside:
+                bits |= r[3]
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            out["reasons"] = [n for n, b in names.items() if bits & b]
+        return out
+
+
+def make_clock_sampler(kind, gpu_index):
+    if kind == "none":
+        return None
+    if kind == "nvml":
+        try:
+            return NvmlClockSampler(gpu_index)
+        except Exception:
+            pass
+    return ClockSampler(gpu_index)
 
 
 def measured_peak_gbs():
@@ -431,7 +503,7 @@ def run_b200(args):
         def step():
             return env._sim_impl(env.env_properties, B, state, acts, TAU, TAU, out=out, layout=layout)
 
-        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        sampler = make_clock_sampler(args.clock_sampler, local_rank) if (sample_clocks and rank == 0) else None
         for _ in range(n_warm):
             step()
         barrier()

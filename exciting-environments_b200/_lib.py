@@ -76,6 +76,14 @@ class ExenvEpilogueArgs(C.Structure):
                 ("reward", C.c_void_p), ("truncated", C.c_void_p), ("terminated", C.c_void_p)]
 
 
+class ExenvGymArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("state", C.c_void_p * MAX_PHYS), ("ref", C.c_void_p * MAX_PHYS),
+                ("hold_steps", C.c_void_p), ("rng", C.c_void_p),
+                ("hold_steps_min", C.c_int32), ("hold_steps_max", C.c_int32), ("force_new", C.c_int32),
+                ("reserved_", C.c_int32),
+                ("reward", C.c_void_p), ("truncated", C.c_void_p), ("terminated", C.c_void_p)]
+
+
 class ExenvScheduleInfo(C.Structure):
     _fields_ = [("n_save", C.c_int64), ("n_steps", C.c_int64), ("n_tiles", C.c_int32), ("act_cap", C.c_int32),
                 ("save_cap", C.c_int32), ("tile_steps", C.c_int32)]
@@ -92,7 +100,7 @@ class ExenvResetArgs(C.Structure):
 SYMBOLS = [
     "exenv_abi_version", "exenv_last_error", "exenv_env_dims", "exenv_launch_count", "exenv_plan_create",
     "exenv_plan_destroy", "exenv_step", "exenv_sim_ahead_shape", "exenv_sim_ahead", "exenv_sim_ahead_host",
-    "exenv_reset_pack", "exenv_schedule_build", "exenv_epilogue", "exenv_trunc_thresholds", "exenv_sim_ahead_prepare",
+    "exenv_reset_pack", "exenv_schedule_build", "exenv_epilogue", "exenv_trunc_thresholds", "exenv_sim_ahead_prepare", "exenv_gym_epilogue",
 ]
 
 
@@ -133,6 +141,7 @@ def lib():
         L.exenv_reset_pack.argtypes = [C.c_void_p, C.POINTER(ExenvResetArgs), C.c_void_p]
         L.exenv_env_dims.argtypes = [C.c_int32, C.POINTER(ExenvDims)]
         L.exenv_epilogue.argtypes = [C.c_void_p, C.POINTER(ExenvEpilogueArgs), C.c_void_p]
+        L.exenv_gym_epilogue.argtypes = [C.c_void_p, C.POINTER(ExenvGymArgs), C.c_void_p]
         L.exenv_schedule_build.argtypes = [C.POINTER(ExenvDesc), C.c_int64, C.c_double, C.c_double, C.c_int32,
                                            C.POINTER(ExenvScheduleInfo), C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]

@@ -584,9 +584,9 @@ class CoreEnvironment:
                               action_stepsize, epilogue=True, **kw)
 
     # ---- reward / truncated / terminated of materialised states ------------------------------------------------------
-    def _epilogue_impl(self, phys_leaves, ref_leaves, n):
+    def _epilogue_impl(self, phys_leaves, ref_leaves, n, env_properties=None):
         """generate_reward / generate_truncated / generate_terminated over `n` states given as flat leaves."""
-        plan = self._plan()
+        plan = self._plan(env_properties, n if env_properties is not None else None)
         dev, dt = self.device, self.dtype
         a = _lib.ExenvEpilogueArgs()
         a.batch = n
@@ -688,6 +688,28 @@ class CoreEnvironment:
         )
         obs, st = self._step_impl(env_properties, 1, self._wrap1(state), self._as(action_norm, (1, self.action_dim)))
         return obs[0], self._unwrap1(st)
+
+    # single-environment epilogue (e.g. pendulum_env.py:297-309, 381-390; read by gym_wrapper.py:53-58): the batched
+    # kernel with one state
+    def _epilogue1(self, state, env_properties):
+        st = self._wrap1(state)
+        phys = [getattr(st.physical_state, n) for n in self.PHYS_FIELDS]
+        refs = [getattr(st.reference, n) for n in self.PHYS_FIELDS]
+        return self._epilogue_impl(phys, refs, 1, env_properties)
+
+    def generate_reward(self, state, action, env_properties):
+        """Reward of one environment's state, shape ``(1,)`` (reference ``jnp.array([reward])``)."""
+        return self._epilogue1(state, env_properties)[0]
+
+    def generate_truncated(self, state, env_properties):
+        """``abs(observation) > 1`` of one environment, shape ``(n_trunc,)`` (fluid tank: ``[False]``; PMSM: current
+        magnitude beyond 1, shape ``(1,)``)."""
+        return self._epilogue1(state, env_properties)[1][0]
+
+    def generate_terminated(self, state, reward, env_properties):
+        """``reward == 0``, shape ``(1,)`` (fluid tank: ``[False]``; PMSM: the truncated flag).  ``reward`` is the value
+        ``generate_reward`` returned for this state (recomputed here: the three hooks share one kernel)."""
+        return self._epilogue1(state, env_properties)[2]
 
     def sim_ahead(self, init_state, actions, env_properties, obs_stepsize, action_stepsize):
         actions = self._as(actions)

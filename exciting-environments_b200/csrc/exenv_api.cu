@@ -623,6 +623,38 @@ int exenv_epilogue(exenv_plan_t plan, const ExenvEpilogueArgs *a, void *stream) 
                                        : launch_epilogue_f32(*plan, *a, (cudaStream_t)stream);
 }
 
+int exenv_gym_epilogue(exenv_plan_t plan, const ExenvGymArgs *a, void *stream) {
+  if (!plan || !a) {
+    set_error("exenv_gym_epilogue: NULL plan/args");
+    return EXENV_ERR_NULL;
+  }
+  EX_ON_DEVICE(plan)
+  if (a->batch < 0) {
+    set_error("exenv_gym_epilogue: negative batch");
+    return EXENV_ERR_INVALID;
+  }
+  if (a->batch == 0) return EXENV_OK;
+  if (plan->per_env) {
+    set_error("exenv_gym_epilogue supports shared parameters only");
+    return EXENV_ERR_UNSUPPORTED;
+  }
+  for (int d = 0; d < plan->dims.n_phys; ++d)
+    if (!a->state[d] || (plan->desc.n_control > 0 && !a->ref[d])) {
+      set_error("exenv_gym_epilogue: state / reference leaf %d is NULL", d);
+      return EXENV_ERR_NULL;
+    }
+  if (a->hold_steps && !a->rng) {
+    set_error("exenv_gym_epilogue: hold_steps without rng");
+    return EXENV_ERR_NULL;
+  }
+  if (a->hold_steps && a->hold_steps_max <= a->hold_steps_min) {
+    set_error("exenv_gym_epilogue: hold_steps_max must exceed hold_steps_min");
+    return EXENV_ERR_INVALID;
+  }
+  return plan->desc.dtype == EXENV_F64 ? launch_gym_epilogue_f64(*plan, *a, (cudaStream_t)stream)
+                                       : launch_gym_epilogue_f32(*plan, *a, (cudaStream_t)stream);
+}
+
 int exenv_sim_ahead_shape(exenv_plan_t plan, int64_t n_actions, double obs_stepsize, double action_stepsize,
                           int64_t *n_save, int64_t *n_steps) {
   if (!plan) {

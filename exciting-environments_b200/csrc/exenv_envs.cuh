@@ -584,6 +584,69 @@ EX_HD void pmsm_clip(T a0, T a1, T eps, T omega_el, T u_dc, T adv, const T *an, 
   *uq_out = vq * half_dc;
 }
 
+// ---- counter-based random numbers for the device-side reference generator -----------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): four 32-bit words per (128-bit counter, 64-bit key).  The GymWrapper reference
+// generator (reference gym_wrapper.py:170-192) draws a fresh random initial state per environment whenever a hold
+// counter runs out; JAX's threefry bit stream cannot be reproduced without JAX, so parity is statistical: same
+// distributions (init_state of each environment), one independent stream per environment (key) and draw (counter).
+EX_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+template <typename T>
+EX_HD T u01_from_bits(uint32_t x) {  // uniform in [0, 1) with 24 random bits (enough for a reference value)
+  return (T)(x >> 8) * (T)(1.0 / 16777216.0);
+}
+
+// A random initial physical state as init_state(env_properties, rng) draws it: uniform(-1, 1) per normalised field,
+// de-normalised (pendulum_env.py:271-276 and the same lines of the other environments); fluid tank uniform(0, 1)
+// (fluid_tank_env.py:227); PMSM: currents uniform in the disc of radius i_max reflected into the permitted box,
+// epsilon / omega_el uniform in their ranges, zero buffers, torque from the currents (pmsm_env.py:402-456).
+// u[0..7]: uniform [0, 1) numbers.
+template <class Env, typename T>
+EX_HD void random_physical_state(const T *u, const T *p, const typename Env::Aux &aux, T *s) {
+  const T *pn = p + Env::NSTATIC;
+  if constexpr (Env::IS_PMSM) {
+    const T r = Mth<T>::sqrt(u[0]), phi = Cst<T>::two_pi() * u[1];
+    T sp, cp;
+    Mth<T>::sincos(phi, &sp, &cp);
+    T imax = Mth<T>::abs(pn[6]);
+    imax = Mth<T>::abs(pn[7]) > imax ? Mth<T>::abs(pn[7]) : imax;
+    imax = Mth<T>::abs(pn[8]) > imax ? Mth<T>::abs(pn[8]) : imax;
+    imax = Mth<T>::abs(pn[9]) > imax ? Mth<T>::abs(pn[9]) : imax;
+    auto relu = [](T x) { return x > (T)0 ? x : (T)0; };
+    const T xd = r * cp * imax, xq = r * sp * imax;
+    const T id = xd - (T)2 * relu(xd - pn[7]) + (T)2 * relu(-xd + pn[6]);
+    const T iq = xq - (T)2 * relu(xq - pn[9]) + (T)2 * relu(-xq + pn[8]);
+    s[0] = (T)0;
+    s[1] = (T)0;
+    s[2] = denorm_mm<T>((T)2 * u[2] - (T)1, pn[4], pn[5]);
+    s[3] = id;
+    s[4] = iq;
+    s[5] = Env::template torque<false>(id, iq, p, aux);
+    s[6] = denorm_mm<T>((T)2 * u[3] - (T)1, pn[12], pn[13]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < Env::D; ++i) {
+      const T z = Env::ID == 2 ? u[i] : (T)2 * u[i] - (T)1;
+      s[i] = denorm_mm<T>(z, pn[2 * i], pn[2 * i + 1]);
+    }
+  }
+}
+
 // ---- observation / reward / flags ------------------------------------------------------------------------------
 // Base observation (without reference entries): e.g. pendulum_env.py:311-329; PMSM pmsm_env.py:898-919 (order
 // i_d, i_q, omega_el, torque, cos eps, sin eps, u_d_buffer, u_q_buffer -- not the order of `_obs_description`).

@@ -85,6 +85,8 @@ int launch_reset_f32(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_
 int launch_reset_f64(const ExenvPlan &plan, const ExenvResetArgs &a, cudaStream_t stream);
 int launch_epilogue_f32(const ExenvPlan &plan, const ExenvEpilogueArgs &a, cudaStream_t stream);
 int launch_epilogue_f64(const ExenvPlan &plan, const ExenvEpilogueArgs &a, cudaStream_t stream);
+int launch_gym_epilogue_f32(const ExenvPlan &plan, const ExenvGymArgs &a, cudaStream_t stream);
+int launch_gym_epilogue_f64(const ExenvPlan &plan, const ExenvGymArgs &a, cudaStream_t stream);
 int launch_sim_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_sim_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);

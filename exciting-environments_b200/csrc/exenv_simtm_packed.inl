@@ -10,7 +10,12 @@
 // Scope: environments marked env_packable (straight-line right-hand side: mass-spring-damper), shared parameters,
 // control_state == [], optionally the fused reward / truncated / terminated outputs.  Everything else runs the scalar
 // kernel of exenv_simtm.inl, which this file mirrors step for step.
-template <class Env, int SOLVER, int W, int V, bool EPI>
+//
+// Zero-order-hold actions: a two-entry window {action q, action q + 1} of PREPARED actions in registers plus the raw
+// action q + 2 in flight.  Every regular step reads at most two consecutive indices and advances q by 0 or 1; the rare
+// steps that touch 3-4 indices or jump further (the accumulated fp32 solver time produces a handful per trajectory)
+// take a second copy of the step body that loads its actions straight from global memory.
+template <class Env, int SOLVER, int V, bool EPI>
 __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
     simtm_packed_kernel(const __grid_constant__ SimTmK<float> a, const __grid_constant__ KParams<float> kp,
                         const __grid_constant__ SimTmHostPre<Env, float> hp) {
@@ -41,7 +46,7 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   const P *pn = pq + Env::NSTATIC;
   typename EnvP::Aux aux{};
 
-  P s0[VV][D], y[VV][NODE], f[VV][NODE], last[VV][NST];
+  P s0[VV][D], y[VV][NODE], f[VV][NODE];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     T tmp[V];
@@ -56,8 +61,6 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
       y[vv][i] = s0[vv][i];
       f[vv][i] = P(0.0f);
     }
-#pragma unroll
-    for (int i = 0; i < NST; ++i) last[vv][i] = P(0.0f);
   }
   NormFma<P> nf[D];
 #pragma unroll
@@ -70,55 +73,77 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
     }
   }
 
-  // ---- window of prepared ZOH actions (see exenv_simtm.inl) ------------------------------------------------------
+  // ---- window of prepared ZOH actions ----------------------------------------------------------------------------------
   const int q_max = (int)a.n_actions - 1;
-  TmFetch<P, A, W> win[VV];
-  T pend[V][A];  // raw action of staged index wbase + W, as loaded: it is packed when it is consumed, not before
-  int wbase = 0;
-  const T *ap = a.actions + b * A;
-  int qn = 0;
   const unsigned act_stride = (unsigned)(a.B * A);
-  constexpr int PF_AHEAD = 6;
-  auto load_next = [&](T (*raw)[A]) {
-    load_vec<T, V * A>(&raw[0][0], ap);
-    if (qn + PF_AHEAD <= q_max) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)PF_AHEAD * act_stride));
-    if (qn < q_max) ap += act_stride;
-    ++qn;
-  };
-  auto prepare = [&](int q, const T (*raw)[A], int k) {
+  const T *act0 = a.actions + b * A;  // this thread's V * A scalars of action 0; action q is q * act_stride further
+  constexpr int PF_AHEAD = 6;         // solver steps between the L2 prefetch of an action row segment and its load
+  auto load_raw = [&](int q, T (*raw)[A]) {  // indices past the end re-read the last action (never used)
     q = q < q_max ? q : q_max;
+    load_vec<T, V * A>(&raw[0][0], act0 + (size_t)q * act_stride);
+  };
+  auto prep = [&](const T (*raw)[A], P (*u)[A]) {
 #pragma unroll
     for (int vv = 0; vv < VV; ++vv) {
       P rp[A];
 #pragma unroll
       for (int c = 0; c < A; ++c) rp[c] = P(raw[2 * vv][c], raw[2 * vv + 1][c]);
-      prepare_action<EnvP, P>((long)q, rp, s0[vv], pq, pre, 0, a.n_actions, P(0.0f), P(0.0f), win[vv].uw[k]);
+      prepare_action<EnvP, P>(0L, rp, s0[vv], pq, pre, 0, a.n_actions, P(0.0f), P(0.0f), u[vv]);
     }
   };
-#pragma unroll
-  for (int k = 0; k < W; ++k) {
-    T raw[V][A];
-    load_next(raw);
-    prepare(k, raw, k);
-  }
-  load_next(pend);
-  bool pend_valid = true;
-  auto slide_to = [&](int base) {
-#pragma unroll 1
-    while (wbase < base) {
-      if (!pend_valid) load_next(pend);
+  P u0[VV][A], u1[VV][A];  // prepared actions wbase, wbase + 1
+  T pend[V][A];            // raw action wbase + 2, requested one step before its first possible use
+  int wbase = 0;
+  auto resync = [&](int base) {  // window := {base, base + 1}, pend := base + 2, by direct loads
+    T r0[V][A], r1[V][A];
+    load_raw(base, r0);
+    load_raw(base + 1, r1);
+    load_raw(base + 2, pend);
+    prep(r0, u0);
+    prep(r1, u1);
+    wbase = base;
+  };
+  auto advance_to = [&](int base) {  // warp-uniform
+    if (base == wbase + 1) {
 #pragma unroll
       for (int vv = 0; vv < VV; ++vv)
 #pragma unroll
-        for (int k = 0; k + 1 < W; ++k)
-#pragma unroll
-          for (int c = 0; c < A; ++c) win[vv].uw[k][c] = win[vv].uw[k + 1][c];
+        for (int c = 0; c < A; ++c) u0[vv][c] = u1[vv][c];
+      prep(pend, u1);
       ++wbase;
-      prepare(wbase + W - 1, pend, W - 1);
-      pend_valid = false;
+      load_raw(wbase + 2, pend);
+      // the segment this thread will load PF_AHEAD steps from now starts its trip from DRAM to L2 here
+      if (wbase + 2 + PF_AHEAD <= q_max)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(act0 + (size_t)(wbase + 2 + PF_AHEAD) * act_stride));
+    } else if (base != wbase) {
+      resync(base);
     }
+  };
+  // the two fetch objects of exenv_sim_core.cuh: the window (stage offset 0 / 1), and direct loads for the rare steps
+  struct PairFetch {
+    const P (*u0)[A];
+    const P (*u1)[A];
+    int vv, wbase;
+    __device__ __forceinline__ void stage(uint64_t w, int s, P *u) const {
+      const bool hi = (unsigned)(w >> (32 + 2 * s)) & 1u;
 #pragma unroll
-    for (int vv = 0; vv < VV; ++vv) win[vv].wbase = wbase;
+      for (int c = 0; c < A; ++c) u[c] = hi ? u1[vv][c] : u0[vv][c];
+    }
+    __device__ __forceinline__ void operator()(int idx, P *u) const {
+#pragma unroll
+      for (int c = 0; c < A; ++c) u[c] = idx > wbase ? u1[vv][c] : u0[vv][c];
+    }
+  };
+  auto direct_fetch = [&](int vv) {
+    return [&, vv](int idx, P *u) {
+      idx = idx < q_max ? idx : q_max;
+      T raw[2][A];
+      load_vec<T, 2 * A>(&raw[0][0], act0 + (size_t)idx * act_stride + 2 * vv * A);
+      P rp[A];
+#pragma unroll
+      for (int c = 0; c < A; ++c) rp[c] = P(raw[0][c], raw[1][c]);
+      prepare_action<EnvP, P>(0L, rp, s0[vv], pq, pre, 0, a.n_actions, P(0.0f), P(0.0f), u);
+    };
   };
 
   // ---- saves: stash the step's first save per pair, one vector store per leaf / observation group afterwards -----
@@ -150,8 +175,6 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
     te = terminated_of<Env, T>((T)0, t0);
   };
   auto sink_pair = [&](int vv, long sidx, const P *st) {
-#pragma unroll
-    for (int i = 0; i < NST; ++i) last[vv][i] = st[i];
     if (sidx == step_first_save) {
 #pragma unroll
       for (int i = 0; i < NST; ++i) stash[vv][i] = st[i];
@@ -240,10 +263,11 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   sched.init(a.steps, smem_raw);
   {
     const uint64_t w0 = sched.chunk(0)->w;
-    slide_to(sched_base(w0));
+    resync(sched_base(w0));
     if constexpr (SOLVER == EXENV_TSIT5) {
 #pragma unroll
-      for (int vv = 0; vv < VV; ++vv) sim_first_derivative<EnvP, P>(w0, y[vv], f[vv], pq, pre, aux, win[vv]);
+      for (int vv = 0; vv < VV; ++vv)
+        sim_first_derivative<EnvP, P>(w0, y[vv], f[vv], pq, pre, aux, PairFetch{u0, u1, vv, wbase});
     }
   }
   const int n_steps = (int)a.n_steps;
@@ -255,29 +279,25 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   for (int k = 0; k < n_in; ++k, ++sr) {
     const uint64_t w = sr->w;
     const P dt = P(sr->dt);
-    slide_to(sched_base(w));
+    // consumes the action that left for DRAM one step ago and requests the next one
+    advance_to(sched_base(w));
     SaveRec<T> rec;
 #pragma unroll
     for (int j = 0; j < (SOLVER == EXENV_EULER ? 1 : 7); ++j) rec.v[j] = sr->wts[j];
-    if (!pend_valid) {
-      load_next(pend);
-      pend_valid = true;
-    }
     step_first_save = save_idx;
     long si = save_idx;
-    if (W > 2 && SOLVER == EXENV_TSIT5 && sched_dmax(w) <= 1) {
+    if (sched_dmax(w) <= 1) {
 #pragma unroll
       for (int vv = 0; vv < VV; ++vv) {
         si = save_idx;
-        const TmFetchPair<P, A, W> pair{win[vv]};
-        sim_one_step<EnvP, SOLVER, P>(w, dt, y[vv], f[vv], pq, pre, aux, rec, a.recs, si, pair,
+        sim_one_step<EnvP, SOLVER, P>(w, dt, y[vv], f[vv], pq, pre, aux, rec, a.recs, si, PairFetch{u0, u1, vv, wbase},
                                       [&](long sidx, const P *st) { sink_pair(vv, sidx, st); });
       }
-    } else {
+    } else {  // rare: a step that reads three or four consecutive actions
 #pragma unroll
       for (int vv = 0; vv < VV; ++vv) {
         si = save_idx;
-        sim_one_step<EnvP, SOLVER, P>(w, dt, y[vv], f[vv], pq, pre, aux, rec, a.recs, si, win[vv],
+        sim_one_step<EnvP, SOLVER, P>(w, dt, y[vv], f[vv], pq, pre, aux, rec, a.recs, si, direct_fetch(vv),
                                       [&](long sidx, const P *st) { sink_pair(vv, sidx, st); });
       }
     }
@@ -287,56 +307,41 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   }
   }
 
-  // ---- last_state and the fresh solver.init derivative at (t1, y_last) --------------------------------------------
+  // ---- last_state (core_env.py:484-488) = the last saved sample, read back from the trajectory rows this thread has
+  // just written (nothing is carried through the loop for it), and the fresh solver.init derivative at (t1, y_last) ----
   const int q_last = (int)(a.n_actions - 1);
   const bool want_k = SOLVER == EXENV_TSIT5 && a.klast[0];
-  if (want_k && q_last > wbase + W - 1) slide_to(q_last - (W - 1));
-  (void)pend_valid;
-  T sl[V][D], fi[V][NODE];
+  T sl[D][V];
 #pragma unroll
-  for (int vv = 0; vv < VV; ++vv) {
-    P slp[D];
-    staged_to_fields<EnvP, P>(last[vv], s0[vv][D - 1], slp);
+  for (int d = 0; d < D; ++d) {
+    const T *src = a.traj[d] + (size_t)(a.n_save - 1) * Bu + b;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      sl[2 * vv][d] = slp[d].x;
-      sl[2 * vv + 1][d] = slp[d].y;
-    }
-    if (want_k) {
+    for (int v = 0; v < V; ++v) sl[d][v] = src[v];
+    if (a.last[d]) store_vec<T, V>(a.last[d] + b, sl[d]);
+  }
+  if (want_k) {
+    T fi[NODE][V];
+#pragma unroll
+    for (int vv = 0; vv < VV; ++vv) {
       P u[A], yl[NODE], fp[NODE];
-      win[vv](q_last, u);
+      direct_fetch(vv)(q_last, u);  // the ZOH closure at t1: clamped to the last action
 #pragma unroll
-      for (int i = 0; i < NODE; ++i) yl[i] = last[vv][i];
+      for (int i = 0; i < NODE; ++i) yl[i] = P(sl[i][2 * vv], sl[i][2 * vv + 1]);
       sim_rhs<EnvP, P>(yl, u, pq, pre, aux, fp);
 #pragma unroll
       for (int i = 0; i < NODE; ++i) {
-        fi[2 * vv][i] = fp[i].x;
-        fi[2 * vv + 1][i] = fp[i].y;
+        fi[i][2 * vv] = fp[i].x;
+        fi[i][2 * vv + 1] = fp[i].y;
       }
     }
-  }
 #pragma unroll
-  for (int d = 0; d < D; ++d)
-    if (a.last[d]) {
-      T col[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) col[v] = sl[v][d];
-      store_vec<T, V>(a.last[d] + b, col);
-    }
-  if (want_k) {
-#pragma unroll
-    for (int i = 0; i < NODE; ++i) {
-      T col[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) col[v] = fi[v][i];
-      store_vec<T, V>(a.klast[i] + b, col);
-    }
+    for (int i = 0; i < NODE; ++i) store_vec<T, V>(a.klast[i] + b, fi[i]);
   }
 }
 
 // Launch (the argument block is the scalar kernel's; the launcher in exenv_simtm.inl has already checked alignment and
 // that the batch splits into groups of V).
-template <class Env, int SOLVER, int W, int V, bool EPI>
+template <class Env, int SOLVER, int V, bool EPI>
 static int launch_simtm_packed_v(const SimTmK<float> &a, const KParams<float> &kp, long batch, cudaStream_t stream) {
   const long threads = (batch + V - 1) / V;
   const int nthr = simtm_block_threads();
@@ -347,7 +352,7 @@ static int launch_simtm_packed_v(const SimTmK<float> &a, const KParams<float> &k
     set_error("sim_ahead (time-major, packed): degenerate normalisation range for the fused truncation flags");
     return EXENV_ERR_INVALID;
   }
-  simtm_packed_kernel<Env, SOLVER, W, V, EPI><<<grid, nthr, tm_sched_smem_bytes<float>(SIMTM_THREADS), stream>>>(a, kp, hp);
+  simtm_packed_kernel<Env, SOLVER, V, EPI><<<grid, nthr, tm_sched_smem_bytes<float>(SIMTM_THREADS), stream>>>(a, kp, hp);
   g_launch_count++;
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

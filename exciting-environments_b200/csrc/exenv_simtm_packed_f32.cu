@@ -10,10 +10,7 @@ template <class Env, int SOLVER, int V, bool EPI>
 static int launch_simtm_packed(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
   const SimTmK<float> a = simtm_args<Env, float>(plan, x, sch);
   const KParams<float> kp = make_kparams<float>(plan);
-  if (sch.win_need <= 2) return launch_simtm_packed_v<Env, SOLVER, 2, V, EPI>(a, kp, x.batch, stream);
-  if (sch.win_need <= 4) return launch_simtm_packed_v<Env, SOLVER, 4, V, EPI>(a, kp, x.batch, stream);
-  set_error("sim_ahead (time-major): a solver step needs %d consecutive actions (> 4)", sch.win_need);
-  return EXENV_ERR_UNSUPPORTED;
+  return launch_simtm_packed_v<Env, SOLVER, V, EPI>(a, kp, x.batch, stream);
 }
 
 template <class Env>

@@ -340,6 +340,113 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpiK<T> a, const KP
   if (a.term) a.term[b] = terminated_of<Env, T>(rw, t0);
 }
 
+// GymWrapper.gym_step after vmap_step (reference gym_wrapper.py:111-126): update_ref -- where an environment's hold
+// counter has run out, the tracked reference fields take the physical state of a freshly drawn random initial state and
+// a new hold time is drawn (:170-192) -- then reward / terminated / truncated against the UPDATED reference.  One thread
+// per environment; random numbers from Philox4x32-10 keyed per environment (rng[2 b] = key, rng[2 b + 1] = draw counter).
+template <typename T>
+struct GymK {
+  long B;
+  const T *s[EXENV_MAX_PHYS];
+  T *ref[EXENV_MAX_PHYS];
+  int32_t *hold;
+  uint64_t *rng;
+  int hold_min, hold_max, force_new;
+  T *reward;
+  uint8_t *trunc;
+  uint8_t *term;
+  int n_control;
+  int control[EXENV_MAX_CONTROL];
+};
+
+template <class Env, typename T>
+__global__ void __launch_bounds__(256) gym_epilogue_kernel(const GymK<T> a, const KParams<T> kp, const LutView<T> lut) {
+  constexpr int D = Env::D, O = Env::O;
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const T *p = kp.v;
+  T s[D], r[D], ob[O + EXENV_MAX_CONTROL];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    s[d] = __ldg(a.s[d] + b);
+    r[d] = a.n_control > 0 ? a.ref[d][b] : (T)0;
+  }
+  if (a.hold && a.n_control > 0) {
+    int h = a.hold[b];
+    if (a.force_new || h == 0) {
+      const uint64_t key = a.rng[2 * b], ctr = a.rng[2 * b + 1];
+      uint32_t w[8];
+      philox4x32_10((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, w);
+      philox4x32_10((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), 1u, 0u, w + 4);
+      T u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = u01_from_bits<T>(w[i]);
+      typename Env::Aux aux{};
+      if constexpr (Env::IS_PMSM) aux.lut = lut;
+      T fresh[D];
+      random_physical_state<Env, T>(u, p, aux, fresh);
+      for (int j = 0; j < a.n_control; ++j) {
+        const int f = a.control[j];
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          if (d == f) {
+            r[d] = fresh[d];
+            a.ref[d][b] = fresh[d];
+          }
+      }
+      const uint32_t span = (uint32_t)(a.hold_max > a.hold_min ? a.hold_max - a.hold_min : 1);
+      h = a.hold_min + (int)(w[7] % span);  // jax.random.randint(minval, maxval): maxval exclusive
+      a.rng[2 * b + 1] = ctr + 1;
+    }
+    a.hold[b] = a.force_new ? h : h - 1;
+  }
+  observe<Env, T>(s, p, ob);
+#pragma unroll
+  for (int j = 0; j < EXENV_MAX_CONTROL; ++j)
+    if (j < a.n_control) ob[O + j] = norm_field<Env, T>(a.control[j], r, p);
+  const int nt = trunc_dim<Env>(a.n_control);
+  bool t0 = false;
+#pragma unroll
+  for (int i = 0; i < O + EXENV_MAX_CONTROL; ++i)
+    if (i < nt) {
+      const bool tv = trunc_entry<Env, T>(i, s, ob, p);
+      if (i == 0) t0 = tv;
+      if (a.trunc) a.trunc[b * nt + i] = tv;
+    }
+  const T rw = a.n_control > 0 ? reward_of<Env, T>(s, r, p, a.n_control, a.control) : (T)0;
+  if (a.reward) a.reward[b] = rw;
+  if (a.term) a.term[b] = terminated_of<Env, T>(rw, t0);
+}
+
+template <class Env, typename T>
+static int launch_gym_epilogue_t(const ExenvPlan &plan, const ExenvGymArgs &x, cudaStream_t stream) {
+  GymK<T> a{};
+  a.B = x.batch;
+  for (int d = 0; d < Env::D; ++d) {
+    a.s[d] = (const T *)x.state[d];
+    a.ref[d] = (T *)x.ref[d];
+  }
+  a.hold = x.hold_steps;
+  a.rng = x.rng;
+  a.hold_min = x.hold_steps_min;
+  a.hold_max = x.hold_steps_max;
+  a.force_new = x.force_new;
+  a.reward = (T *)x.reward;
+  a.trunc = x.truncated;
+  a.term = x.terminated;
+  a.n_control = plan.desc.n_control;
+  for (int j = 0; j < EXENV_MAX_CONTROL; ++j) a.control[j] = plan.desc.control[j];
+  const unsigned grid = (unsigned)((x.batch + 255) / 256);
+  gym_epilogue_kernel<Env, T><<<grid, 256, 0, stream>>>(a, make_kparams<T>(plan), make_lut_view<T>(plan));
+  g_launch_count++;
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("exenv_gym_epilogue launch failed: %s", cudaGetErrorString(e));
+    return EXENV_ERR_CUDA;
+  }
+  return EXENV_OK;
+}
+
 template <class Env, typename T>
 static int launch_epilogue_t(const ExenvPlan &plan, const ExenvEpilogueArgs &x, cudaStream_t stream) {
   EpiK<T> a{};
@@ -374,6 +481,22 @@ int EXENV_CAT(launch_epilogue_, EXENV_SFX)(const ExenvPlan &plan, const ExenvEpi
     case EXENV_CART_POLE: return launch_epilogue_t<CartPole<T>, T>(plan, x, st);
     case EXENV_ACROBOT: return launch_epilogue_t<Acrobot<T>, T>(plan, x, st);
     case EXENV_PMSM: return launch_epilogue_t<Pmsm<T, false>, T>(plan, x, st);
+  }
+  set_error("unknown env %d", plan.desc.env);
+  return EXENV_ERR_INVALID;
+}
+
+int EXENV_CAT(launch_gym_epilogue_, EXENV_SFX)(const ExenvPlan &plan, const ExenvGymArgs &x, cudaStream_t st) {
+  using T = EXENV_REAL;
+  switch (plan.desc.env) {
+    case EXENV_PENDULUM: return launch_gym_epilogue_t<Pendulum<T>, T>(plan, x, st);
+    case EXENV_MASS_SPRING_DAMPER: return launch_gym_epilogue_t<MassSpringDamper<T>, T>(plan, x, st);
+    case EXENV_FLUID_TANK: return launch_gym_epilogue_t<FluidTank<T>, T>(plan, x, st);
+    case EXENV_CART_POLE: return launch_gym_epilogue_t<CartPole<T>, T>(plan, x, st);
+    case EXENV_ACROBOT: return launch_gym_epilogue_t<Acrobot<T>, T>(plan, x, st);
+    case EXENV_PMSM:
+      if (plan.desc.flags & EXENV_FLAG_SATURATED) return launch_gym_epilogue_t<Pmsm<T, true>, T>(plan, x, st);
+      return launch_gym_epilogue_t<Pmsm<T, false>, T>(plan, x, st);
   }
   set_error("unknown env %d", plan.desc.env);
   return EXENV_ERR_INVALID;

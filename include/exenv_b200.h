@@ -14,6 +14,8 @@
  *                            e.g. pendulum_env.py:261-295) and vmap_generate_state_from_observation :689-705
  *   exenv_epilogue        <- vmap(generate_reward / truncated / terminated) gym_wrapper.py:117-126 and
  *                            vmap_generate_rew_trunc_term_ahead core_env.py:618-647 on materialised states
+ *   exenv_gym_epilogue    <- GymWrapper.gym_step after its vmap_step: update_ref / generate_new_ref (gym_wrapper.py:
+ *                            170-192, per-environment hold counters, device-side counter RNG) + the three epilogue vmaps
  *   exenv_sim_ahead_host  <- the same vmap_sim_ahead call made with HOST buffers (what a CPU-JAX caller holds);
  *                            pipelines H2D / kernel / D2H over batch chunks.
  *
@@ -203,6 +205,30 @@ typedef struct ExenvEpilogueArgs {
   uint8_t *terminated;               /* optional (batch,) */
 } ExenvEpilogueArgs;
 int exenv_epilogue(exenv_plan_t plan, const ExenvEpilogueArgs *args, void *stream);
+
+/* ---- GymWrapper.gym_step after vmap_step: reference generator + reward / terminated / truncated ------------------------
+ * gym_wrapper.py:111-126: `update_ref` (:170-175) -- for every environment whose hold counter is 0 the tracked
+ * (control_state) reference fields become the physical state of a freshly drawn random initial state and a new hold time
+ * is drawn in [hold_steps_min, hold_steps_max) (`generate_new_ref`, :177-192), then every counter is decremented --
+ * followed by generate_reward / generate_terminated / generate_truncated against the UPDATED reference (the observation
+ * returned by the step itself still shows the previous reference, as in the reference).  Random numbers: Philox4x32-10,
+ * one stream per environment -- rng[2 b] is the environment's key, rng[2 b + 1] its draw counter (advanced by the
+ * kernel).  Distributions are those of each environment's init_state(rng); the bit stream is not JAX's threefry.
+ * hold_steps == NULL switches the generator off (plain epilogue).  force_new != 0: draw for every environment and do not
+ * decrement (GymWrapper.reset with rng_ref, :156-160).  Shared parameters only. */
+typedef struct ExenvGymArgs {
+  int64_t batch;
+  const void *state[EXENV_MAX_PHYS]; /* D leaves (B,) */
+  void *ref[EXENV_MAX_PHYS];         /* D reference leaves (B,), control_state leaves updated in place */
+  int32_t *hold_steps;               /* (B,) in/out, or NULL */
+  uint64_t *rng;                     /* (B, 2) in/out, required iff hold_steps != NULL */
+  int32_t hold_steps_min, hold_steps_max;
+  int32_t force_new, reserved_;
+  void *reward;        /* optional (B,) */
+  uint8_t *truncated;  /* optional (B, n_trunc) */
+  uint8_t *terminated; /* optional (B,) */
+} ExenvGymArgs;
+int exenv_gym_epilogue(exenv_plan_t plan, const ExenvGymArgs *args, void *stream);
 
 /* Host-only diagnostic (needs no CUDA device): the emulated diffrax.diffeqsolve time bookkeeping for `desc` -- per
  * solver step the packed ZOH-index word and step length, per saved sample the dense-output abscissa, and the tile

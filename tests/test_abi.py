@@ -28,7 +28,8 @@ def test_header_symbols_are_exported(excenvs):
 
 def test_struct_layouts_match_header(excenvs):
     L = excenvs._lib
-    names = ["ExenvDesc", "ExenvDims", "ExenvStepArgs", "ExenvSimArgs", "ExenvResetArgs", "ExenvScheduleInfo"]
+    names = ["ExenvDesc", "ExenvDims", "ExenvStepArgs", "ExenvSimArgs", "ExenvResetArgs", "ExenvScheduleInfo",
+             "ExenvEpilogueArgs", "ExenvGymArgs"]
     prog = '#include <stdio.h>\n#include "exenv_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     prog += 'printf("off_p %zu\\n", offsetof(ExenvDesc, p));printf("off_pp %zu\\n", offsetof(ExenvDesc, pp));'
@@ -80,3 +81,24 @@ def test_product_never_imports_the_oracle():
     assert len(files) > 10
     for f in files:
         assert not pat.search(f.read_text()), f
+
+
+def test_xla_ffi_shim_compiles_against_the_api_stub_and_covers_every_entry_point(excenvs):
+    """csrc/xla_ffi_shim.cc cannot be built against the real XLA headers in this image (no jax); it is compiled against
+    tests/ffi_stub (a stub of the part of the public xla::ffi API it uses) so that handler names, arity and the C-ABI
+    structs they fill stay consistent with include/exenv_b200.h, and every launching entry point has a handler that
+    jax_ffi.py registers."""
+    import re
+
+    root = HEADER.parent.parent
+    shim = root / "exciting-environments_b200" / "csrc" / "xla_ffi_shim.cc"
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", str(root / "tests" / "ffi_stub"),
+                        "-I", "/usr/local/cuda/include", str(shim)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    src = shim.read_text()
+    handlers = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", src))
+    from exciting_environments_b200 import jax_ffi
+
+    assert handlers == set(jax_ffi.TARGETS.values())
+    for entry in ("exenv_step(", "exenv_sim_ahead(", "exenv_reset_pack(", "exenv_epilogue(", "exenv_gym_epilogue("):
+        assert entry in src, entry

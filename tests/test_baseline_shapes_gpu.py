@@ -216,16 +216,28 @@ def test_config4_pmsm_saturated_two_chunks_against_oracle(excenvs, layout, act_s
             tol, sens = HORIZON_TOL[dtype], None
         else:
             tol, sens = _sens_tol(orc, cur, sub_acts[:, c * CH:(c + 1) * CH], dtype, ref, scales)
+        # The electrical angle integrates the constant omega_el whatever the actions are, so its fp32 accumulation noise
+        # can be measured directly: the fp32 oracle against the fp64 oracle (the other fields cannot be compared across
+        # precisions: the zero-order-hold index lags differently in fp32 and fp64).  After 2500 steps that
+        # noise is ~1.5e-4 of pi -- the bound for epsilon is twice the reference formula's own distance from fp64.
+        ref64 = O.Oracle("pmsm", solver=O.TSIT5, dtype=np.float64, saturated=True, motor="BRUSA").sim_ahead(
+            [np.asarray(x, np.float64) for x in cur], sub_acts[:, c * CH:(c + 1) * CH].astype(np.float64), orc.tau, orc.tau)
+        eps_noise = traj_err(_unwrap_to(ref["traj"][2], ref64["traj"][2], 2 * np.pi), ref64["traj"][2], scales[2])
         own = {}
         for name, r, sc in zip(e.PHYS_FIELDS, ref["traj"], scales):
             got = np_(getattr(states.physical_state, name)[tix])
             own[name] = got
             row = _errors(name, got, r, sc, dtype, 2 * np.pi if name == "epsilon" else None)
             row["chunk"] = c
+            bound = max(tol, 2 * eps_noise) if name == "epsilon" else tol
+            if name == "epsilon":
+                row["fp32_reference_formula_vs_fp64"] = eps_noise
             rows_all.append(row)
-            assert row["normalised"] <= tol, (c, row, tol)
-        got_obs = np_(obs[tix])  # (cos eps, sin eps are continuous across the wrap)
-        assert traj_err(got_obs.reshape(N_SUB, -1), ref["obs"].reshape(N_SUB, -1), 1.0) <= max(tol, 2e-4)
+            assert row["normalised"] <= bound, (c, row, bound)
+        # observations: cos(eps), sin(eps) (continuous across the wrap) carry the angle's accumulation noise in radians
+        got_obs = np_(obs[tix])
+        obs_bound = max(2 * tol, 2.1 * eps_noise * np.pi)
+        assert traj_err(got_obs.reshape(N_SUB, -1), ref["obs"].reshape(N_SUB, -1), 1.0) <= obs_bound
         # flags: the reference expression on the returned states, subset on the host + consistency on the full batch
         leaves = [own[n] if n in ("i_d", "i_q") else None for n in e.PHYS_FIELDS]
         assert np.array_equal(np_(trunc[tix]).astype(np.uint8), flags_from_states(orc, leaves))

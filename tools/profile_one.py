@@ -17,6 +17,8 @@ blk = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 tm = len(sys.argv) > 9 and sys.argv[9] == "tm"
 epi = len(sys.argv) > 10 and sys.argv[10] == "epi"  # fused reward / truncated / terminated outputs
 dtype = torch.float32 if dt == "f32" else torch.float64
+import os
+SCALE = float(os.environ.get("EXENV_PROFILE_ACT_SCALE", "1.0"))  # e.g. 0.02: PMSM voltages that keep the currents inside the flux maps
 kw = dict(saturated=True, motor_variant=ex.MotorVariant.BRUSA) if name == "pmsm_sat" else {}
 env = ENVS[name](batch_size=B, solver=ex.Tsit5() if solver == "tsit5" else ex.Euler(), dtype=dtype, **kw)
 env.max_steps = None
@@ -24,11 +26,11 @@ _, state = env.vmap_reset(rng=0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if kind == "sim":
     if tm:
-        actions = (torch.rand((T, B, env.action_dim), device="cuda", dtype=dtype) * 2 - 1).permute(1, 0, 2)
+        actions = ((torch.rand((T, B, env.action_dim), device="cuda", dtype=dtype) * 2 - 1) * SCALE).permute(1, 0, 2)
         out = dict(obs=torch.empty((T + 1, B, env.obs_dim), device="cuda", dtype=dtype),
                    traj=[torch.empty((T + 1, B), device="cuda", dtype=dtype) for _ in range(env.physical_state_dim)])
     else:
-        actions = torch.rand((B, T, env.action_dim), device="cuda", dtype=dtype) * 2 - 1
+        actions = (torch.rand((B, T, env.action_dim), device="cuda", dtype=dtype) * 2 - 1) * SCALE
         out = dict(obs=torch.empty((B, T + 1, env.obs_dim), device="cuda", dtype=dtype),
                    traj=[torch.empty((B, T + 1), device="cuda", dtype=dtype) for _ in range(env.physical_state_dim)])
     fn = lambda: env._sim_impl(env.env_properties, B, state, actions, env.tau, env.tau, tile_steps=tile,
