@@ -594,11 +594,17 @@ def run_b200(args):
             st64.physical_state = env64.PhysicalState(*[x[:64].to(dev) for x in h_state])
             chk = env64.vmap_sim_ahead(st64, h_act[:64].to(dev), TAU, TAU)[0].cpu()
             ok = bool(torch.equal(h_obs[:64], chk))
+            sec = float(tt.item()) / n_e2e
             e2e = {"value": world * B * T_STEPS * n_e2e / float(tt.item()), "unit": "env-steps/s",
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
                    "batch_per_gpu": B, "matches_device_path": ok, "cpu_affinity": affinity,
-                   "how": "exenv_sim_ahead_host: pinned host buffers, chunked H2D / kernel / D2H on 3 streams, "
-                          "wall clock around the blocking C call (max over ranks)"}
+                   "h2d_gbs_per_gpu": h2d / sec / 1e9, "d2h_gbs_per_gpu": d2h / sec / 1e9,
+                   "bound": "the host link: every pass moves h2d + d2h bytes per GPU between pinned host memory and "
+                            "HBM (copies of both directions overlap the kernel on 3 streams); the kernel itself needs "
+                            "well under 1 % of this time and there is no collective -- at N > 1 the ranks share the "
+                            "host's memory / PCIe root bandwidth, which is what limits the e2e scaling curve",
+                   "how": "exenv_sim_ahead_host: pinned host buffers, chunked H2D / kernel / D2H on 3 streams kept in "
+                          "the plan, wall clock around the blocking C call (max over ranks)"}
             del h_obs, h_traj, h_act
         except Exception as exc:  # e.g. not enough host memory to pin the buffers
             e2e = {"value": None, "unit": "env-steps/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,

@@ -84,6 +84,10 @@ class CoreEnvironment:
     N_ODE: int = 0
     N_OBS: int = 0
     ODE_FIELDS: tuple = ()  # PhysicalState fields that form the ODE state, in solver order
+    # PMSM's _ode_solver_simulate_ahead returns an all-NaN reference whatever init_state.reference holds
+    # (pmsm_env.py:688-701), so observations' *_ref columns, rewards and last_state.reference of a PMSM sim_ahead are
+    # NaN upstream; reproduced (SURVEY Appendix C style quirk, pinned by tests/test_sim_gpu.py)
+    SIM_AHEAD_NAN_REFERENCE: bool = False
 
     State = _State
     EnvProperties = _EnvProperties
@@ -488,8 +492,12 @@ class CoreEnvironment:
         a.tile_steps, a.block_envs = tile_steps, block_envs
         a.layout = _lib.LAYOUT_TIME_MAJOR if tm else _lib.LAYOUT_BATCH_MAJOR
         refs = None
+        if self.SIM_AHEAD_NAN_REFERENCE:
+            init_ref = self.PhysicalState(*[self._constant("nan", B)] * D)
+        else:
+            init_ref = init_state.reference
         if self.control_state:
-            refs = [self._as(getattr(init_state.reference, n), (B,)) for n in self.PHYS_FIELDS]
+            refs = [self._as(getattr(init_ref, n), (B,)) for n in self.PHYS_FIELDS]
         for i in range(D):
             a.state_in[i] = phys_in[i].data_ptr()
             a.traj[i] = traj[i].data_ptr()
@@ -522,7 +530,7 @@ class CoreEnvironment:
                 return t.expand(B, NS)
             return t.unsqueeze(1).expand(B, NS, *t.shape[1:])
 
-        ref_t = [over_time(getattr(init_state.reference, n)) for n in self.PHYS_FIELDS]
+        ref_t = [over_time(getattr(init_ref, n)) for n in self.PHYS_FIELDS]
         states = self.State(
             physical_state=self.PhysicalState(*traj),
             PRNGKey=over_time(init_state.PRNGKey),
@@ -538,7 +546,7 @@ class CoreEnvironment:
             physical_state=self.PhysicalState(*last),
             PRNGKey=torch.as_tensor(init_state.PRNGKey, device=dev).to(dt),
             additions=self.Additions(solver_state=klast, active_solver_state=self._constant("one", B)),
-            reference=self.PhysicalState(*[torch.as_tensor(getattr(init_state.reference, n), device=dev).to(dt)
+            reference=self.PhysicalState(*[torch.as_tensor(getattr(init_ref, n), device=dev).to(dt)
                                            for n in self.PHYS_FIELDS]),
         )
         if epilogue:

@@ -118,73 +118,34 @@ EX_HD int lut_cell_regular(T g0, T inv_d, int n, T x) {
   return (gf > (T)0) ? ((gf < (T)(n - 2)) ? (int)gf : n - 2) : 0;  // NaN -> 0
 }
 
-// The flux-map cell an environment's currents were last found in, as the bilinear coefficients of the six maps on that
-// cell: value_q(s, t) = a_q + bx_q s + (by_q + cxy_q s) t with s, t the offsets into the cell in units of its widths
-// (the four-corner form sum_corners c * w of RegularGridInterpolator expanded once per cell; 3 FMAs per map instead of
-// 4 products + the weights, and -- the point -- no shared-memory traffic while the currents stay in the cell: the
-// 24 corner reads per look-up with random cells per lane were the kernel's bottleneck, profiles/README.md).
-// (slo, shi] x (tlo, thi] is the set of offsets for which searchsorted(side="left") - 1, clipped to [0, n - 2], picks
-// this very cell: (0, 1] in the interior, open-ended at the map edges (linear extrapolation).  A look-up outside it
-// refills the cache through lut_cell (exact index semantics); offsets within rounding distance of a cell boundary may
-// use the neighbouring cell, where the interpolant has the same value up to rounding (it is continuous).
-template <typename T>
-struct LutCellCache {
-  T a[6], bx[6], by[6], cxy[6];
-  T x0 = (T)0, rx = (T)0, y0 = (T)0, ry = (T)0;
-  T slo = (T)0, shi = (T)-1, tlo = (T)0, thi = (T)-1;  // empty: the first look-up refills
-};
-
-template <typename T>
-EX_HD void lut_cell_refill(const LutView<T> &L, LutCellCache<T> &c, T id, T iq) {
-  int i, j;
-  if (L.wx && L.regular) {  // device blob, equidistant grids: index by arithmetic, origin + reciprocal width in one read
-    i = lut_cell_regular<T>(L.gx0, L.inv_dx, L.nx, id);
-    j = lut_cell_regular<T>(L.gy0, L.inv_dy, L.ny, iq);
-  } else {
-    i = lut_cell<T>(L.gx, L.nx, L.inv_dx, id, L.regular);
-    j = lut_cell<T>(L.gy, L.ny, L.inv_dy, iq, L.regular);
+// The look-up of the instruction-bound fp32 kernels: cell by arithmetic (equidistant grids of the device blob), origin +
+// reciprocal width in one read per dimension, the four-corner form of the reference.  No branch, no state: 26
+// shared-memory reads.  (A per-thread cache of the current cell's bilinear coefficients was measured and dropped: with
+// 32 lanes in 32 different cells some lane leaves its cell in almost every evaluation, so the warp issues the refill
+// path anyway, and the 32 extra registers cost a resident CTA: 1.04e10 / 1.24e10 env-steps/s with the cache against
+// 1.60e10 / 1.74e10 without, full-range / 2 % voltages, profiles/README.md.)
+template <typename T, int FIRST, int COUNT>
+EX_HD void lut_eval_direct(const LutView<T> &L, T id, T iq, T *out) {
+  if (!(L.wx && L.regular)) {  // host harness / irregular grids: the exact-index path
+    lut_eval<T, FIRST, COUNT>(L, id, iq, out);
+    return;
   }
-  if (L.wx) {
-    c.x0 = L.wx[4 * i];
-    c.rx = L.wx[4 * i + 2];
-    c.y0 = L.wy[4 * j];
-    c.ry = L.wy[4 * j + 2];
-  } else {
-    c.x0 = L.gx[i];
-    c.y0 = L.gy[j];
-    c.rx = (T)1 / (L.gx[i + 1] - L.gx[i]);
-    c.ry = (T)1 / (L.gy[j + 1] - L.gy[j]);
-  }
-  const T inf = (T)INFINITY;
-  c.slo = i == 0 ? -inf : (T)0;
-  c.shi = i == L.nx - 2 ? inf : (T)1;
-  c.tlo = j == 0 ? -inf : (T)0;
-  c.thi = j == L.ny - 2 ? inf : (T)1;
+  const int i = lut_cell_regular<T>(L.gx0, L.inv_dx, L.nx, id);
+  const int j = lut_cell_regular<T>(L.gy0, L.inv_dy, L.ny, iq);
+  const T s = (id - L.wx[4 * i]) * L.wx[4 * i + 2], t = (iq - L.wy[4 * j]) * L.wy[4 * j + 2];
+  const T s1 = (T)1 - s, t1 = (T)1 - t;
+  const T w00 = s1 * t1, w01 = s1 * t, w10 = s * t1, w11 = s * t;
   const T *c00 = L.cells + (i * L.ny + j) * L.cs;
   const T *c10 = c00 + L.ny * L.cs;
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const T v00 = c00[q], v01 = c00[L.cs + q], v10 = c10[q], v11 = c10[L.cs + q];
-    c.a[q] = v00;
-    c.bx[q] = v10 - v00;
-    c.by[q] = v01 - v00;
-    c.cxy[q] = (v11 - v10) - (v01 - v00);
+  for (int q = 0; q < COUNT; ++q) {
+    T v = c00[FIRST + q] * w00;
+    v = fma_(c00[L.cs + FIRST + q], w01, v);
+    v = fma_(c10[FIRST + q], w10, v);
+    v = fma_(c10[L.cs + FIRST + q], w11, v);
+    out[q] = v;
   }
 }
-
-template <typename T, int FIRST, int COUNT>
-EX_HD void lut_eval_cached(const LutView<T> &L, LutCellCache<T> &c, T id, T iq, T *out) {
-  T s = (id - c.x0) * c.rx, t = (iq - c.y0) * c.ry;
-  if (!(s > c.slo && s <= c.shi && t > c.tlo && t <= c.thi)) {
-    lut_cell_refill<T>(L, c, id, iq);
-    s = (id - c.x0) * c.rx;
-    t = (iq - c.y0) * c.ry;
-  }
-#pragma unroll
-  for (int q = 0; q < COUNT; ++q)
-    out[q] = fma_(t, fma_(s, c.cxy[FIRST + q], c.by[FIRST + q]), fma_(s, c.bx[FIRST + q], c.a[FIRST + q]));
-}
-
 struct NoAux {};
 
 template <typename T>
@@ -192,7 +153,6 @@ struct PmsmAux {
   T omega_el;  // constant over a step / a sim_ahead call (pmsm_env.py:546, 639)
   int deadtime;
   LutView<T> lut;
-  mutable LutCellCache<T> cell;  // saturated maps: the cell of the last look-up (FAST paths)
 };
 
 // ---- Pendulum (pendulum/pendulum_env.py) -------------------------------------------------------------------
@@ -220,6 +180,8 @@ struct Pendulum {
     else dy[1] = div_inv<false, T>(u[0] + q.lmg * Mth<T>::sin(y[0]), q.ml2);
   }
   EX_HD static void post(T *y) { y[0] = wrap_pi<T>(y[0]); }  // :188, :241
+  template <typename U>
+  using rebind = Pendulum<U>;
   EX_HD static bool is_angle(int f) { return f == 0; }
   EX_HD static void default_norm_state(T *z) {  // :265-268
     z[0] = (T)1;
@@ -294,7 +256,6 @@ template <>
 struct env_packable<MassSpringDamper<float>> {
   static constexpr bool value = true;
 };
-
 // Environments whose trajectory kernels keep pre-scaled actions in the zero-order-hold window and evaluate
 // Env::rhs_sim(y, u_prescaled, pre, dy) instead of Env::rhs<true> (sim_rhs / prepare_action in exenv_sim_core.cuh).
 template <class Env>
@@ -327,11 +288,13 @@ struct FluidTank {
   // :97-106  p = base_area, orifice_area, c_d, g
   template <bool FAST>
   EX_HD static void rhs(const T *y, const T *u, const T *, const Pre &q, const Aux &, T *dy) {
-    const T h = y[0] < (T)0 ? (T)0 : y[0];
+    const T h = relu_(y[0]);
     if constexpr (FAST) dy[0] = div_mul<T>(u[0], q.Ab) - q.coef * Mth<T>::sqrt(q.two_g * h);
     else dy[0] = div_inv<false, T>(u[0], q.Ab) - q.coef * Mth<T>::sqrt(q.two_g * h);
   }
-  EX_HD static void post(T *y) { y[0] = y[0] < (T)0 ? (T)0 : y[0]; }  // :146, :196
+  EX_HD static void post(T *y) { y[0] = relu_(y[0]); }  // :146, :196
+  template <typename U>
+  using rebind = FluidTank<U>;
   EX_HD static bool is_angle(int) { return false; }
   EX_HD static void default_norm_state(T *z) { z[0] = (T)0; }  // :221-224
 };
@@ -377,6 +340,8 @@ struct CartPole {
     dy[3] = d_om;
   }
   EX_HD static void post(T *y) { y[2] = wrap_pi<T>(y[2]); }  // :229
+  template <typename U>
+  using rebind = CartPole<U>;
   EX_HD static bool is_angle(int f) { return f == 2; }
   EX_HD static void default_norm_state(T *z) {  // :317-322
     z[0] = z[1] = z[3] = (T)0;
@@ -393,6 +358,10 @@ struct Acrobot {
   // :171-197  p = g, l_1, l_2, m_1, m_2, l_c1, l_c2, I_1, I_2 ; y = theta_1, theta_2, omega_1, omega_2
   struct Pre {};
   EX_HD static Pre precompute(const T *) { return Pre{}; }
+  template <class SrcPre>
+  EX_HD static Pre from_scalar(const SrcPre &) { return Pre{}; }
+  template <typename U>
+  using rebind = Acrobot<U>;
   template <bool FAST>
   EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &, const Aux &, T *dy) {
     const T g = p[0], l1 = p[1], m1 = p[3], m2 = p[4], lc1 = p[5], lc2 = p[6], I1 = p[7], I2 = p[8];
@@ -443,6 +412,25 @@ struct Acrobot {
   }
 };
 
+// The transcendental environments: sine / cosine through the packed Cody-Waite + polynomial pair (exenv_math.cuh:
+// sincos2), square roots, reciprocal seeds, signs, clamps and the angle wrap per lane, everything else packed.
+template <>
+struct env_packable<Pendulum<float>> {
+  static constexpr bool value = true;
+};
+template <>
+struct env_packable<FluidTank<float>> {
+  static constexpr bool value = true;
+};
+template <>
+struct env_packable<CartPole<float>> {
+  static constexpr bool value = true;
+};
+template <>
+struct env_packable<Acrobot<float>> {
+  static constexpr bool value = true;
+};
+
 // ---- PMSM (pmsm/pmsm_env.py) -----------------------------------------------------------------------------------
 // PhysicalState fields: 0 u_d_buffer, 1 u_q_buffer, 2 epsilon, 3 i_d, 4 i_q, 5 torque, 6 omega_el (:281-291)
 // ODE state y = (i_d, i_q, epsilon) (:555).  p = p, r_s, l_d, l_q, psi_p, u_dc, deadtime.
@@ -472,13 +460,13 @@ struct Pmsm {
       dy[1] = div_inv<FAST, T>(u[1] - w * (l_d * id + psi_p) - r_s * iq, q_.lq);
     } else if constexpr (FAST && sizeof(T) == 4) {  // :487-507 nonlinear_ode, instruction-bound fp32 kernels (fp64 keeps
                                                     // the reference's order of operations: its per-step tolerance is 1e-12)
-      // Look-up through the cell cache; then, instead of forming inv(L) (LU with partial pivoting + two solves) and three
+      // Look-up (lut_eval_direct); then, instead of forming inv(L) (LU with partial pivoting + two solves) and three
       // matrix-vector products, ONE right-hand side b = -r_s i + u - omega J Psi is eliminated with the same pivoting
       // (inv(L) b = inv(L) (-r_s i) + inv(L) u + (-inv(L) J Psi) omega up to rounding), its two divisions by pivots as
       // Newton-refined reciprocals (exenv_math.cuh: rcp_nr, ~1 ulp).  The differential inductances are well conditioned
       // (L_dd, L_qq dominate by >10x): the derivative moves by a few ulp, far inside the per-step tolerance.
       T q[6];
-      lut_eval_cached<T, 0, 6>(aux.lut, aux.cell, id, iq, q);
+      lut_eval_direct<T, 0, 6>(aux.lut, id, iq, q);
       const T rhs0 = fma_(w, q[5], fma_(-r_s, id, u[0]));   // u_d - r_s i_d + omega Psi_q
       const T rhs1 = fma_(-w, q[4], fma_(-r_s, iq, u[1]));  // u_q - r_s i_q - omega Psi_d
       const bool swap = Mth<T>::abs(q[2]) > Mth<T>::abs(q[0]);
@@ -530,7 +518,7 @@ struct Pmsm {
       return (T)1.5 * p[0] * (p[4] + (p[2] - p[3]) * id) * iq;
     } else {
       T q[2];
-      if constexpr (FAST && sizeof(T) == 4) lut_eval_cached<T, 4, 2>(aux.lut, aux.cell, id, iq, q);  // usually a hit
+      if constexpr (FAST && sizeof(T) == 4) lut_eval_direct<T, 4, 2>(aux.lut, id, iq, q);
       else lut_eval<T, 4, 2>(aux.lut, id, iq, q);
       return (T)1.5 * p[0] * (q[0] * iq - q[1] * id);
     }

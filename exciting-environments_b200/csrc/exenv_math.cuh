@@ -341,6 +341,110 @@ EX_HD f32x2 denorm_mm<f32x2>(f32x2 z, f32x2 mn, f32x2 mx) {
 }
 #endif
 
+#if defined(__CUDACC__)
+// ---- packed transcendental helpers: what the right-hand sides of pendulum / fluid tank / cart-pole / acrobot need ----
+EX_HD int f32_bits(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(x);
+#else
+  int i;
+  memcpy(&i, &x, 4);
+  return i;
+#endif
+}
+EX_HD float f32_from_bits(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  float x;
+  memcpy(&x, &i, 4);
+  return x;
+#endif
+}
+// sin and cos of two angles at once.  Cody-Waite reduction by pi/2 with three FMAs on the packed pipe (k = rint(2x/pi)
+// by the magic-number addition; pi/2 = HI + MID + LO to ~2^-76, the products exact inside the FMAs), both minimax
+// polynomials of the Cephes single-precision sinf / cosf on |r| <= pi/4 as FFMA2 chains, and only the quadrant fix-up
+// (two selects and two sign flips) per lane: ~16 packed + ~12 scalar instructions for two angles, against ~25 scalar
+// instructions per angle for CUDA's sincosf.  Maximum error 1.6 ulp for |x| < 1e5 (tests/test_hostcheck.py; CUDA's
+// sinf / cosf: 1.5 ulp); larger arguments, inf and nan take libm per lane.
+EX_HD void sincos2(f32x2 x, f32x2 *sn, f32x2 *cs) {
+  const f32x2 kf = fma_(x, f32x2(0.63661977236758134f), f32x2(12582912.0f));
+  const f32x2 k = kf + f32x2(-12582912.0f);
+  f32x2 r = fma_(k, f32x2(-1.5707963705062866f), x);
+  r = fma_(k, f32x2(4.371138828673793e-08f), r);
+  r = fma_(k, f32x2(1.7151245100058819e-15f), r);
+  const f32x2 z = r * r;
+  f32x2 ps = fma_(z, f32x2(-1.9515295891e-4f), f32x2(8.3321608736e-3f));
+  ps = fma_(ps, z, f32x2(-1.6666654611e-1f));
+  const f32x2 s = fma_(r * z, ps, r);
+  f32x2 pc = fma_(z, f32x2(2.443315711809948e-5f), f32x2(-1.388731625493765e-3f));
+  pc = fma_(pc, z, f32x2(4.166664568298827e-2f));
+  const f32x2 c = fma_(z * z, pc, fma_(z, f32x2(-0.5f), f32x2(1.0f)));
+  auto lane = [](float kfl, float sl, float cl, float *so, float *co) {
+    const int q = f32_bits(kfl);  // the low mantissa bits of x * 2/pi + 1.5 * 2^23 hold rint(x * 2/pi)
+    const float a = (q & 1) ? cl : sl, b = (q & 1) ? sl : cl;
+    *so = f32_from_bits(f32_bits(a) ^ ((q & 2) << 30));
+    *co = f32_from_bits(f32_bits(b) ^ (((q + 1) & 2) << 30));
+  };
+  lane(kf.x, s.x, c.x, &sn->x, &cs->x);
+  lane(kf.y, s.y, c.y, &sn->y, &cs->y);
+  // beyond the reduction's range (or inf / nan): libm, per lane.  One warp-wide vote decides whether anybody has to go
+  // there, so that the common case costs a uniform branch instead of four divergent ones.
+  const bool big = !(::fabsf(x.x) < 100000.0f) || !(::fabsf(x.y) < 100000.0f);
+#if defined(__CUDA_ARCH__)
+  if (__any_sync(__activemask(), big)) {
+    if (!(::fabsf(x.x) < 100000.0f)) ::sincosf(x.x, &sn->x, &cs->x);
+    if (!(::fabsf(x.y) < 100000.0f)) ::sincosf(x.y, &sn->y, &cs->y);
+  }
+#else
+  if (big) {
+    if (!(::fabsf(x.x) < 100000.0f)) {
+      sn->x = ::sinf(x.x);
+      cs->x = ::cosf(x.x);
+    }
+    if (!(::fabsf(x.y) < 100000.0f)) {
+      sn->y = ::sinf(x.y);
+      cs->y = ::cosf(x.y);
+    }
+  }
+#endif
+}
+template <>
+struct Mth<f32x2> {
+  static EX_HD f32x2 sin(f32x2 x) {
+    f32x2 s, c;
+    sincos2(x, &s, &c);
+    return s;
+  }
+  static EX_HD f32x2 cos(f32x2 x) {
+    f32x2 s, c;
+    sincos2(x, &s, &c);
+    return c;
+  }
+  static EX_HD void sincos(f32x2 x, f32x2 *s, f32x2 *c) { sincos2(x, s, c); }
+  static EX_HD f32x2 sqrt(f32x2 x) { return f32x2(::sqrtf(x.x), ::sqrtf(x.y)); }
+  static EX_HD f32x2 abs(f32x2 x) { return f32x2(::fabsf(x.x), ::fabsf(x.y)); }
+};
+// Newton-refined reciprocal: the two hardware approximations per lane, the refinement packed
+EX_HD f32x2 rcp_nr(f32x2 d) {
+#if defined(__CUDA_ARCH__)
+  f32x2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return fma_(r, fma_(-d, r, f32x2(1.0f)), r);
+#else
+  return f32x2(1.0f / d.x, 1.0f / d.y);
+#endif
+}
+#endif  // __CUDACC__
+
+// max(x, 0) as the reference writes it for the tank height (jnp.clip(h, 0): NaN stays NaN)
+EX_HD float relu_(float x) { return x < 0.0f ? 0.0f : x; }
+EX_HD double relu_(double x) { return x < 0.0 ? 0.0 : x; }
+#if defined(__CUDACC__)
+EX_HD f32x2 relu_(f32x2 x) { return f32x2(relu_(x.x), relu_(x.y)); }
+#endif
+
 // jnp `%`: C fmod followed by the sign correction (jax.numpy.remainder); SURVEY Appendix A.
 template <typename T>
 EX_HD T pymod(T x, T y) {
@@ -376,6 +480,16 @@ template <typename T>
 EX_HD T sign_of(T v) {
   return (T)((v > (T)0) - (v < (T)0));
 }
+#if defined(__CUDACC__)
+template <>
+EX_HD f32x2 wrap_pi<f32x2>(f32x2 th) {
+  return f32x2(wrap_pi<float>(th.x), wrap_pi<float>(th.y));
+}
+template <>
+EX_HD f32x2 sign_of<f32x2>(f32x2 v) {
+  return f32x2(sign_of<float>(v.x), sign_of<float>(v.y));
+}
+#endif
 
 // ---- Tsit5 (diffrax.Tsit5; Tsitouras 2011).  SURVEY Appendix B.2 --------------------------------------------
 // Stage increments are k_i = f_i * dt (diffrax "vf_prod"); stage states y0 + sum_j a_ij k_j; the solution is the

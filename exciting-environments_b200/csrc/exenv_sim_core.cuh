@@ -4,6 +4,8 @@
 // tests/hostcheck compiles the very same functions for the CPU to validate them against the oracle without a GPU.
 #pragma once
 
+#include <type_traits>
+
 #include "../../include/exenv_b200.h"
 #include "exenv_envs.cuh"
 
@@ -185,14 +187,12 @@ EX_HD void sim_one_step(uint64_t w, T dt, T *y, T *f, const T *p, const typename
   } else {  // diffrax.Tsit5 with FSAL, derivative form (exenv_math.cuh: tsit5_step_f): k holds f_1 .. f_7
 #pragma unroll
     for (int i = 0; i < NODE; ++i) k[0][i] = f[i];
-    tsit5_step_f<T, NODE>(
-        y, dt,
-        [&](int stage, const T *ys, T *fo) {
-          T u[A];
-          fetch_stage_(fetch, w, stage, u, 0);
-          sim_rhs<Env, T>(ys, u, p, pre, aux, fo);
-        },
-        y1, k);
+    auto stage_rhs = [&](int stage, const T *ys, T *fo) {
+      T u[A];
+      fetch_stage_(fetch, w, stage, u, 0);
+      sim_rhs<Env, T>(ys, u, p, pre, aux, fo);
+    };
+    tsit5_step_f<T, NODE>(y, dt, stage_rhs, y1, k);
 #pragma unroll
     for (int i = 0; i < NODE; ++i) f[i] = k[6][i];
   }

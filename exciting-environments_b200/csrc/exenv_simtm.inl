@@ -515,11 +515,11 @@ constexpr int simtm_auto_v() {
   constexpr bool f32 = sizeof(T) == 4, tsit = SOLVER == EXENV_TSIT5;
   if (Env::IS_PMSM) return 1;
   switch (Env::ID) {
-    case 0: return tsit ? (f32 ? 2 : 1) : (f32 ? 4 : 1);  // pendulum
+    case 0: return tsit ? (f32 ? 4 : 1) : (f32 ? 4 : 1);  // pendulum (fp32: packed, profiles/README.md round 2)
     case 1: return tsit ? (f32 ? 4 : 1) : (f32 ? 2 : 1);  // mass-spring-damper
-    case 2: return tsit ? (f32 ? 4 : 1) : (f32 ? 4 : 2);  // fluid tank
-    case 3: return tsit ? 1 : 2;                          // cart-pole
-    default: return tsit ? 1 : (f32 ? 2 : 1);             // acrobot
+    case 2: return tsit ? (f32 ? 2 : 1) : (f32 ? 4 : 2);  // fluid tank
+    case 3: return tsit ? (f32 ? 2 : 1) : 2;              // cart-pole (fp32 Tsit5: one packed pair per thread)
+    default: return tsit ? (f32 ? 2 : 1) : (f32 ? 2 : 1);  // acrobot
   }
 }
 

@@ -15,8 +15,22 @@
 // action q + 2 in flight.  Every regular step reads at most two consecutive indices and advances q by 0 or 1; the rare
 // steps that touch 3-4 indices or jump further (the accumulated fp32 solver time produces a handful per trajectory)
 // take a second copy of the step body that loads its actions straight from global memory.
+// Resident CTAs per SM the register allocation aims at: two-component systems keep four environments per thread in 128
+// registers; the four-component ones (cart-pole, acrobot: seven stage derivatives of four packed components = 56
+// registers per pair) need ~160 registers for one pair per thread.
+template <class Env, int V>
+constexpr int packed_min_blocks() {
+  return Env::NODE >= 4 ? (V == 4 ? 2 : 3) : (V == 4 ? 4 : 5);
+}
+// Solver steps per trip of the step loop: two for the mass-spring-damper (its loop-carried state then ping-pongs
+// between two register sets instead of being copied back after every step: 44 MOVs per thread-step); one for the
+// environments with sine / cosine / reciprocal code, whose step body is several times larger (instruction cache).
+template <class Env>
+constexpr int packed_unroll() {
+  return Env::ID == 1 ? 2 : 1;
+}
 template <class Env, int SOLVER, int V, bool EPI>
-__global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
+__global__ void __launch_bounds__(SIMTM_THREADS, packed_min_blocks<Env, V>())
     simtm_packed_kernel(const __grid_constant__ SimTmK<float> a, const __grid_constant__ KParams<float> kp,
                         const __grid_constant__ SimTmHostPre<Env, float> hp) {
   using T = float;
@@ -275,7 +289,9 @@ __global__ void __launch_bounds__(SIMTM_THREADS, V == 4 ? 4 : 5)
   for (int i0 = 0; i0 < n_steps; i0 += TM_CHUNK) {  // 32 steps per staged chunk of schedule records
   const TmStep<T> *sr = sched.chunk(i0 / TM_CHUNK);
   const int n_in = min(TM_CHUNK, n_steps - i0);
-#pragma unroll 1
+  // two steps per trip: the loop-carried state (y, FSAL derivative, window) ping-pongs between two register sets
+  // instead of being copied back at the end of every step (44 MOVs per thread-step in the single-step loop)
+#pragma unroll(packed_unroll<Env>())
   for (int k = 0; k < n_in; ++k, ++sr) {
     const uint64_t w = sr->w;
     const P dt = P(sr->dt);

@@ -2,7 +2,15 @@
 // environments marked env_packable, fp32, two or four environments per thread (exenv_simtm_packed.inl).
 #include "exenv_simtm_common.cuh"
 
+// Built as two objects (Makefile: -DEXENV_PACKED_PART=1 / 2) so that the two halves compile in parallel.
+#ifndef EXENV_PACKED_PART
+#define EXENV_PACKED_PART 0  // 0: everything in one object
+#endif
+
 namespace exenv {
+
+int launch_simtm_packed_f32_part2(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch,
+                                  cudaStream_t stream, int v);
 
 #include "exenv_simtm_packed.inl"
 
@@ -30,13 +38,36 @@ static int packed_dispatch(const ExenvPlan &plan, const ExenvSimArgs &x, const S
 
 // v = 2 or 4 environments per thread; the caller (exenv_simtm.inl: launch_simtm_fast) has checked alignment, that the
 // batch splits into groups of v, shared parameters and control_state == [].
-int launch_simtm_packed_f32(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream,
-                            int v) {
+#if EXENV_PACKED_PART != 2
+int launch_simtm_packed_f32_part1(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch,
+                                  cudaStream_t stream, int v) {
   switch (plan.desc.env) {
+    case EXENV_PENDULUM: return packed_dispatch<Pendulum<float>>(plan, x, sch, stream, v);
     case EXENV_MASS_SPRING_DAMPER: return packed_dispatch<MassSpringDamper<float>>(plan, x, sch, stream, v);
+    case EXENV_FLUID_TANK: return packed_dispatch<FluidTank<float>>(plan, x, sch, stream, v);
   }
   set_error("no packed-arithmetic trajectory kernel for env %d", plan.desc.env);
   return EXENV_ERR_UNSUPPORTED;
 }
+#endif
+#if EXENV_PACKED_PART != 1
+int launch_simtm_packed_f32_part2(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch,
+                                  cudaStream_t stream, int v) {
+  switch (plan.desc.env) {
+    case EXENV_CART_POLE: return packed_dispatch<CartPole<float>>(plan, x, sch, stream, v);
+    case EXENV_ACROBOT: return packed_dispatch<Acrobot<float>>(plan, x, sch, stream, v);
+  }
+  set_error("no packed-arithmetic trajectory kernel for env %d", plan.desc.env);
+  return EXENV_ERR_UNSUPPORTED;
+}
+#endif
+#if EXENV_PACKED_PART != 2
+int launch_simtm_packed_f32(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream,
+                            int v) {
+  if (plan.desc.env == EXENV_CART_POLE || plan.desc.env == EXENV_ACROBOT)
+    return launch_simtm_packed_f32_part2(plan, x, sch, stream, v);
+  return launch_simtm_packed_f32_part1(plan, x, sch, stream, v);
+}
+#endif
 
 }  // namespace exenv

@@ -181,6 +181,7 @@ class PMSM(CoreEnvironment):
     ACTION_FIELDS = ("u_d", "u_q")
     STATIC_FIELDS = ("p", "r_s", "l_d", "l_q", "psi_p", "u_dc", "deadtime")
     N_ODE, N_OBS = 3, 8
+    SIM_AHEAD_NAN_REFERENCE = True  # pmsm_env.py:688-701
 
     EnvProperties = _PmsmEnvProperties
 

@@ -177,6 +177,17 @@ void hc_norm_forms(long n, int is_f64, const void *x, double mn, double mx, void
     norm_forms_t<float>(n, (const float *)x, (float)mn, (float)mx, (float *)o_mm, (float *)o_inv, (float *)o_fma,
                         (float *)coef);
 }
+// exenv_math.cuh: the packed sine / cosine pair (two angles per call) and the packed Newton reciprocal
+void hc_sincos2(long n, const float *x, float *s, float *c) {
+  for (long i = 0; i + 1 < n; i += 2) {
+    f32x2 sn, cs;
+    sincos2(f32x2(x[i], x[i + 1]), &sn, &cs);
+    s[i] = sn.x;
+    s[i + 1] = sn.y;
+    c[i] = cs.x;
+    c[i + 1] = cs.y;
+  }
+}
 void hc_fmod_two_pi(long n, int is_f64, const void *x, void *fmod_out, void *wrap_out) {
   for (long i = 0; i < n; ++i) {
     if (is_f64) {

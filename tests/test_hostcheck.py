@@ -209,3 +209,33 @@ def test_normalisation_forms(hostcheck_lib, dtype):
             assert coef[1] == 0 and o[2][4] == 0
         if mn == 0:
             assert coef[1] == -1 and o[2][0] == -1
+
+
+def test_packed_sincos_accuracy(hostcheck_lib):
+    """exenv_math.cuh: sincos2 -- the packed (two angles per FFMA2 chain) sine / cosine of the trajectory kernels of the
+    pendulum, cart-pole and acrobot.  The host build performs the same correctly rounded FMAs as the device's FFMA2,
+    so this is the device's result: at most 2 ulp from the exact value for |x| < 1e5 (CUDA's sinf / cosf: 1.5 ulp),
+    including arguments within 1e-4 of the zeros (multiples of pi / 2); huge arguments, inf and nan go to libm."""
+    rng = np.random.default_rng(0)
+    parts = [rng.uniform(-np.pi, np.pi, 400000), rng.uniform(-100, 100, 400000), rng.uniform(-1e5, 1e5, 400000),
+             (np.arange(-2000, 2001)[:, None] * np.pi / 2 + rng.uniform(-1e-3, 1e-3, (4001, 20))).ravel(),
+             (np.arange(-40, 41)[:, None] * np.pi / 2 + rng.uniform(-1e-4, 1e-4, (81, 500))).ravel(),
+             np.array([0.0, -0.0, 1e-30, -1e-30, 1e-8, 0.5, -0.5])]
+    x = np.concatenate(parts).astype(np.float32)
+    if x.size % 2:
+        x = np.concatenate([x, x[:1]])
+    s, c = np.empty_like(x), np.empty_like(x)
+    hostcheck_lib.hc_sincos2(C.c_long(x.size), C.c_void_p(x.ctypes.data), C.c_void_p(s.ctypes.data),
+                             C.c_void_p(c.ctypes.data))
+    xs = x.astype(np.float64)
+    for got, want in ((s, np.sin(xs)), (c, np.cos(xs))):
+        ulp = np.spacing(np.abs(want).astype(np.float32)).astype(np.float64)
+        err = np.abs(got.astype(np.float64) - want) / ulp
+        assert err.max() <= 2.0, (err.max(), x[err.argmax()])
+    big = np.array([2e5, -3e6, 1e9, np.inf, -np.inf, np.nan, 7e7, 1.5e5], np.float32)
+    sb, cb = np.empty_like(big), np.empty_like(big)
+    hostcheck_lib.hc_sincos2(C.c_long(big.size), C.c_void_p(big.ctypes.data), C.c_void_p(sb.ctypes.data),
+                             C.c_void_p(cb.ctypes.data))
+    with np.errstate(invalid="ignore"):
+        assert np.allclose(sb, np.sin(big.astype(np.float64)), rtol=0, atol=2e-7, equal_nan=True)
+        assert np.allclose(cb, np.cos(big.astype(np.float64)), rtol=0, atol=2e-7, equal_nan=True)

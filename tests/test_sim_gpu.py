@@ -293,19 +293,26 @@ def test_standalone_rew_trunc_term_ahead_equals_fused(excenvs, env, ctrl):
     st = random_state(base, B, rng, 0.6, pmsm_gentle=(env == "pmsm"))
     refl = random_state(base, B, rng, 0.6)
     acts = rng.uniform(-1, 1, (B, T, orc.A)) * (0.02 if env == "pmsm" else 1.0)
-    ref = orc.sim_ahead(st, acts, 1e-4, 1e-4, ref=refl if ctrl else None, epilogue=True)
+    # PMSM: the reference's sim_ahead drops init_state.reference and returns NaN references (pmsm_env.py:688-701), so
+    # the *_ref observation columns and the rewards of a PMSM trajectory are NaN upstream -- reproduced and pinned here
+    oracle_ref = [np.full(B, np.nan)] * len(refl) if env == "pmsm" else refl
+    ref = orc.sim_ahead(st, acts, 1e-4, 1e-4, ref=oracle_ref if ctrl else None, epilogue=True)
     e = make_env(excenvs, orc, B)
     s0 = to_state(e, st, refl if ctrl else None)
     a = torch.as_tensor(acts, device="cuda")
     obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(s0, a, 1e-4, 1e-4)
+    if env == "pmsm":
+        assert bool(torch.isnan(obs[..., 8:]).all())  # (the rewards follow from NaN references: compared below)
+        assert bool(torch.isnan(states.reference.i_d).all()) and bool(torch.isnan(last.reference.torque).all())
     rew2, trunc2, term2 = e.vmap_generate_rew_trunc_term_ahead(states, a)
     assert rew2.shape == (B, T, 1) and trunc2.shape == (B, T + 1, orc.n_trunc) and term2.shape == (B, T, 1)
-    assert torch.allclose(rew, rew2, rtol=1e-12, atol=1e-14) and torch.equal(trunc, trunc2) and torch.equal(term, term2)
-    assert np.allclose(np_(rew)[..., 0], ref["reward"], rtol=1e-9, atol=1e-12)
+    assert torch.allclose(rew, rew2, rtol=1e-12, atol=1e-14, equal_nan=True)
+    assert torch.equal(trunc, trunc2) and torch.equal(term, term2)
+    assert np.allclose(np_(rew)[..., 0], ref["reward"], rtol=1e-9, atol=1e-12, equal_nan=True)
     assert np.array_equal(np_(term)[..., 0].astype(np.uint8), ref["terminated"])
     # GymWrapper-style epilogue of a single batched state
     r1, tr1, te1 = e.vmap_generate_reward_truncated_terminated(last)
-    assert torch.allclose(r1[:, 0], rew[:, -1, 0], rtol=1e-12, atol=1e-14) and torch.equal(tr1, trunc[:, -1])
+    assert torch.allclose(r1[:, 0], rew[:, -1, 0], rtol=1e-12, atol=1e-14, equal_nan=True) and torch.equal(tr1, trunc[:, -1])
 
 
 @pytest.mark.parametrize("env", ["mass_spring_damper", "pendulum", "cart_pole", "pmsm"])
@@ -341,18 +348,18 @@ def test_time_major_equals_batch_major(excenvs, env, solver):
 def test_time_major_envs_per_thread_and_fallbacks(excenvs, env, solver):
     """Time-major kernel: 1, 2 or 4 environments per thread (vector accesses) give the same trajectories; a batch
     that does not split evenly falls back to narrower vectors; the fused-epilogue flavour matches the plain one.
-    Bit-identical for the scalar instantiations; the packed-arithmetic instantiation (fp32 mass-spring-damper with 2 or
-    4 environments per thread: FFMA2) performs the same operations but the compiler may contract a different
-    multiply-add pair, so it is compared to rounding."""
+    The packed-arithmetic instantiations (fp32, 2 or 4 environments per thread: FFMA2) perform the same algorithm as
+    the scalar one-environment-per-thread kernel; compared to rounding."""
     rng = np.random.default_rng(23)
     orc = O.Oracle(env, solver=solver, dtype=np.float32)
-    packed = env == "mass_spring_damper"
+    # fp32 kernels with 2 or 4 environments per thread use packed arithmetic (FFMA2; sine / cosine through the packed
+    # polynomial pair): same algorithm as the one-environment-per-thread scalar kernel, values equal to rounding
+    # (amplified along the 150 coarse steps of the chaotic cart-pole)
+    tol = {"mass_spring_damper": 2e-6, "pendulum": 1e-5, "fluid_tank": 5e-6, "cart_pole": 2e-3}[env]
     scales = field_scales(orc)
 
     def same(x, y, scale=1.0):
-        if not packed:
-            return torch.equal(x, y)
-        return ((x - y).abs().max() / scale).item() <= 2e-6
+        return ((x - y).abs().max() / scale).item() <= tol
 
     for B in (4 * 97, 4 * 97 + 2, 4 * 97 + 1):  # V = 4 / 2 / 1 at most
         T = 150

@@ -198,3 +198,77 @@ def test_step_is_cuda_graph_capturable(excenvs):
     torch.cuda.synchronize()
     assert torch.equal(obs_e, obs_g)
     assert torch.equal(s_eager.physical_state.theta, s_out.physical_state.theta)
+
+
+def test_first_sim_ahead_of_a_shape_is_cuda_graph_capturable(excenvs):
+    """exenv_sim_ahead_prepare uploads the time schedule of a call shape ahead of time, so that exenv_sim_ahead itself
+    never allocates or synchronises: the FIRST launch of a shape can be issued inside a stream capture (an XLA custom
+    call).  Without the prepare call a capture gets an error, not a cudaMalloc."""
+    import ctypes as C
+
+    L = excenvs._lib
+    B, T = 512, 37
+    env = excenvs.MassSpringDamper(batch_size=B, solver=excenvs.Tsit5(), dtype=torch.float32)
+    _, s = env.vmap_reset(rng=2)
+    acts = torch.rand((T, B, 1), device="cuda") * 2 - 1
+    leaves = [getattr(s.physical_state, n).contiguous() for n in env.PHYS_FIELDS]
+    obs = torch.zeros((T + 1, B, 2), device="cuda")
+    traj = [torch.zeros((T + 1, B), device="cuda") for _ in range(2)]
+    a = L.ExenvSimArgs()
+    a.batch, a.n_actions, a.obs_stepsize, a.action_stepsize, a.max_steps = B, T, env.tau, env.tau, 4096
+    a.layout = L.LAYOUT_TIME_MAJOR
+    for i in range(2):
+        a.state_in[i], a.traj[i] = leaves[i].data_ptr(), traj[i].data_ptr()
+    a.actions, a.obs = acts.data_ptr(), obs.data_ptr()
+    plan = env._plan().handle
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    # (1) unprepared shape inside a capture: refused
+    g0 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g0, stream=side):
+            rc = L.lib().exenv_sim_ahead(plan, C.byref(a), C.c_void_p(side.cuda_stream))
+    assert rc == -1 and "exenv_sim_ahead_prepare" in L.last_error()
+    # (2) prepared: the very first launch of the shape is captured and replays
+    ns, nst = C.c_int64(), C.c_int64()
+    L.check(L.lib().exenv_sim_ahead_prepare(plan, T, env.tau, env.tau, 0, C.byref(ns), C.byref(nst)))
+    assert ns.value == T + 1
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            L.check(L.lib().exenv_sim_ahead(plan, C.byref(a), C.c_void_p(side.cuda_stream)))
+    g.replay()
+    torch.cuda.synchronize()
+    ref = env.vmap_sim_ahead(s, acts.permute(1, 0, 2), env.tau, env.tau, layout="time_major")[0]
+    assert torch.equal(obs.permute(1, 0, 2), ref)
+
+
+def test_entry_points_run_on_the_plans_device(excenvs):
+    """Every entry point selects the plan's device and restores the calling thread's current device: plan
+    creation, launches, the host-buffer pipeline and plan destruction leave torch's current device alone; with two GPUs
+    an environment on cuda:1 works while cuda:0 is current and gives the same numbers."""
+    import gc
+
+    cur = torch.cuda.current_device()
+    env = excenvs.Pendulum(batch_size=64, solver=excenvs.Tsit5(), dtype=torch.float32, device=f"cuda:{cur}")
+    _, s = env.vmap_reset(rng=1)
+    a = torch.rand((64, 1), device=f"cuda:{cur}") * 2 - 1
+    obs0, s1 = env.vmap_step(s, a)
+    acts = torch.rand((64, 20, 1), device=f"cuda:{cur}") * 2 - 1
+    tr0 = env.vmap_sim_ahead(s, acts, env.tau, env.tau)[0]
+    assert torch.cuda.current_device() == cur
+    if torch.cuda.device_count() >= 2:
+        other = (cur + 1) % torch.cuda.device_count()
+        env2 = excenvs.Pendulum(batch_size=64, solver=excenvs.Tsit5(), dtype=torch.float32, device=f"cuda:{other}")
+        st2 = env2._new_state([getattr(s.physical_state, n).to(f"cuda:{other}") for n in env2.PHYS_FIELDS],
+                              s.PRNGKey.to(f"cuda:{other}"), env2._solver_state_dummy(64),
+                              torch.zeros(64, dtype=torch.bool, device=f"cuda:{other}"),
+                              [getattr(s.reference, n).to(f"cuda:{other}") for n in env2.PHYS_FIELDS])
+        obs2, _ = env2.vmap_step(st2, a.to(f"cuda:{other}"))
+        tr2 = env2.vmap_sim_ahead(st2, acts.to(f"cuda:{other}"), env2.tau, env2.tau)[0]
+        assert torch.cuda.current_device() == cur
+        assert obs2.device.index == other and torch.equal(obs2.cpu(), obs0.cpu()) and torch.equal(tr2.cpu(), tr0.cpu())
+        del env2, st2
+    del env
+    gc.collect()  # _Plan.__del__ -> exenv_plan_destroy
+    assert torch.cuda.current_device() == cur
