@@ -276,7 +276,7 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-KERNELS = {"time_major": ("simtm", "exenv::simtm_packed_kernel<MassSpringDamper<float>, Tsit5, W=4, V=4> (FFMA2)"),
+KERNELS = {"time_major": ("simtm", "exenv::simtm_packed_kernel<MassSpringDamper<float>, Tsit5, V=4> (FFMA2)"),
            "batch_major": ("sim", "exenv::sim_kernel<MassSpringDamper<float>, Tsit5, float>")}
 
 
@@ -425,7 +425,7 @@ def run_extras(ex, torch, dist, dev, rank, world, peaks):
     guarded(step_case, "pendulum Euler vmap_step", ex.Pendulum, E, 1 << 24, 50, "step_kernel<Pendulum<float>, Euler, VEC=4>",
             "step_pendulum_euler_f32")
     guarded(sim_case, "pendulum Euler vmap_sim_ahead", ex.Pendulum, E, 1 << 20, 1000,
-            "simtm_kernel<Pendulum<float>, Euler, V=4>", "simtm_pendulum_euler_f32")
+            "simtm_packed_kernel<Pendulum<float>, Euler, V=4>", "simtm_pendulum_euler_f32")
     # north-star target 2 = BASELINE configs[3]: PMSM with saturated flux maps, Tsit5, fused epilogue (>= 1e10 on 8 GPUs);
     # 2^17 environments per GPU is the shard of the 2^20 batch on 8 GPUs, 5000 steps as two 2500-step chunks
     guarded(sim_case, "pmsm saturated (BRUSA LUT) Tsit5 vmap_sim_ahead + epilogue", ex.PMSM, T5, 1 << 17, 5000,
@@ -435,7 +435,7 @@ def run_extras(ex, torch, dist, dev, rank, world, peaks):
     for nm, cls in (("cart_pole", ex.CartPole), ("acrobot", ex.Acrobot)):
         guarded(step_case, f"{nm} Euler vmap_step", cls, E, 1 << 22, 200, f"step_kernel<{cls.__name__}<float>, Euler, VEC=4>",
                 f"step_{nm}_euler_f32")
-        guarded(sim_case, f"{nm} Tsit5 vmap_sim_ahead", cls, T5, 1 << 22, 200, f"simtm_kernel<{cls.__name__}<float>, Tsit5>",
+        guarded(sim_case, f"{nm} Tsit5 vmap_sim_ahead", cls, T5, 1 << 22, 200, f"simtm_packed_kernel<{cls.__name__}<float>, Tsit5, V=2>",
                 f"simtm_{nm}_tsit5_f32")
     # BASELINE configs[1], the fp64 half
     guarded(sim_case, "mass_spring_damper Tsit5 vmap_sim_ahead fp64", ex.MassSpringDamper, T5, 1 << 20, 2000,
@@ -638,8 +638,10 @@ def run_b200(args):
                              "ncu": {k: facts.get(k) for k in ("issue_slots_busy", "fma_pipe_busy", "dram_pct_of_peak",
                                                                 "warp_instructions_per_env_step", "source")},
                              "note": "the Tsit5 trajectory kernel sits between the fp32 FMA pipe (7 right-hand sides + dense "
-                                     "output per env-step: 97 fp32 operations as 48.5 packed instructions, pipe 62 % busy) "
-                                     "and HBM (55 % of peak under ncu); see profiles/README.md"},
+                                     "output per env-step: 83 fp32 operations as 41.5 packed instructions, pipe ~62 % busy) "
+                                     "and HBM (~63 % of peak under ncu); 20 back-to-back passes run under the board's "
+                                     "power management (SM clock dips to ~1.75-1.85 GHz), a 3-pass burst is ~7 % faster; "
+                                     "see profiles/README.md"},
                 "other_layout": other, "extra": extra}
         if extra and extra.get("fma_peak") and extra["fma_peak"].get("ffma2_tflops"):
             # the headline kernel against the fp32 FMA pipe as well: packed (FFMA2 / FMUL2 / FADD2) warp instructions per
