@@ -376,13 +376,23 @@ def run_extras(ex, torch, dist, dev, rank, world, peaks):
                 _, st = env.vmap_step(st, acts[t], inplace=True)
             box["s"] = st
 
-        sec, launches = timed(one_pass, 2, warm=1)
+        # The n_steps launches are captured ONCE into a CUDA graph and replayed: at 2^22 environments a step kernel
+        # runs ~45 us, about what one eager vmap_step call costs in Python / ctypes / allocator time, so an eager loop
+        # would time the host (profiles/README.md: 36 us per eager call, 3.9 us per replayed launch).
+        one_pass()
+        torch.cuda.synchronize(dev)
+        graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                one_pass()
+        torch.cuda.synchronize(dev)
+        sec, _ = timed(graph.replay, 3, warm=2)
         D, A, O = env.physical_state_dim, env.action_dim, env.obs_dim
         tsit = isinstance(solver, ex.Tsit5)
         bpe = 4 * (2 * D + A + O + (env.N_ODE if tsit else 0))
-        out.append(entry(name, f"{name}: batch={B}/GPU, {n_steps} vmap_step calls, one launch each, float32", B * n_steps,
-                         sec, launches, bpe, kernel, fact_key))
-        del acts, state, box
+        out.append(entry(name, f"{name}: batch={B}/GPU, {n_steps} vmap_step calls (one launch each, captured once into a "
+                               f"CUDA graph and replayed), float32", B * n_steps, sec, n_steps, bpe, kernel, fact_key))
+        del acts, state, box, graph
 
     def sim_case(name, cls, solver, B, T, kernel, fact_key=None, epilogue=False, chunks=1, dtype=f32, **kw):
         env = cls(batch_size=B, solver=solver, dtype=dtype, device=dev, **kw)

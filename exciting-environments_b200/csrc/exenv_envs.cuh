@@ -115,7 +115,7 @@ EX_HD void lut_eval(const LutView<T> &L, T id, T iq, T *out) {
 template <typename T>
 EX_HD int lut_cell_regular(T g0, T inv_d, int n, T x) {
   const T gf = (x - g0) * inv_d;
-  return (gf > (T)0) ? ((gf < (T)(n - 2)) ? (int)gf : n - 2) : 0;  // NaN -> 0
+  return (int)min_(max_(gf, (T)0), (T)(n - 2));  // clamp, then truncate: no branch; NaN -> 0 (fmax / fmin drop a NaN)
 }
 
 // The look-up of the instruction-bound fp32 kernels: cell by arithmetic (equidistant grids of the device blob), origin +

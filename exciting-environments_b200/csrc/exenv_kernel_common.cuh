@@ -133,9 +133,12 @@ EX_HD void env_step_one(T *s, const T *a, const T *p, typename Env::Aux &aux, T 
 #pragma unroll
     for (int i = 0; i < NODE; ++i) y0[i] = s[i];
   }
-  // Tsit5 (instruction bound): divisions by parameter-only denominators through the prepared reciprocal (correctly
-  // rounded, exenv_math.cuh); Euler (HBM bound, golden-vector replay): the plain IEEE operator
-  constexpr bool FD = SOLVER == EXENV_TSIT5;
+  // Tsit5 (instruction bound): the FAST right-hand sides (prepared reciprocals, Newton-refined divisions, exenv_math.cuh)
+  // in both precisions.  Euler: fp64 keeps the plain IEEE operators (the reference's golden vectors replay on this
+  // path); fp32 uses the FAST forms for cart-pole and acrobot, whose IEEE divisions and cosines made the fp32 Euler step
+  // instruction bound (0.73 / 0.65 of HBM; profiles/README.md round 2) -- the same forms the trajectory kernels use,
+  // inside the 1e-6 per-step tolerance.
+  constexpr bool FD = SOLVER == EXENV_TSIT5 || (sizeof(T) == 4 && (Env::ID == 3 || Env::ID == 4));
   T f0[NODE];
   const typename Env::Pre pre = Env::precompute(p);
   Env::template rhs<FD>(y0, u, p, pre, aux, f0);

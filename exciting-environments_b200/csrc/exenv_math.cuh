@@ -438,6 +438,11 @@ EX_HD f32x2 rcp_nr(f32x2 d) {
 }
 #endif  // __CUDACC__
 
+EX_HD float max_(float a, float b) { return ::fmaxf(a, b); }
+EX_HD double max_(double a, double b) { return ::fmax(a, b); }
+EX_HD float min_(float a, float b) { return ::fminf(a, b); }
+EX_HD double min_(double a, double b) { return ::fmin(a, b); }
+
 // max(x, 0) as the reference writes it for the tank height (jnp.clip(h, 0): NaN stays NaN)
 EX_HD float relu_(float x) { return x < 0.0f ? 0.0f : x; }
 EX_HD double relu_(double x) { return x < 0.0 ? 0.0 : x; }

@@ -525,7 +525,9 @@ constexpr int simtm_auto_v() {
 
 template <class Env, int SOLVER, typename T>
 static int launch_simtm_fast(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
-  constexpr int VMAX = Env::IS_PMSM ? 1 : 4;  // instantiated widths: 1, (2, 4)
+  // instantiated widths: 1, (2, 4).  Four fp64 environments of a four-component system per thread would need > 255
+  // registers (the instantiation spilled and was never the tuned choice): those stop at two.
+  constexpr int VMAX = Env::IS_PMSM ? 1 : ((sizeof(T) == 8 && Env::NODE >= 4) ? 2 : 4);
   int v = x.block_envs > 0 ? x.block_envs : simtm_auto_v<Env, SOLVER, T>();
   if (v > VMAX) v = VMAX;
   if (v == 3) v = 2;
