@@ -473,8 +473,10 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
     L.bytes = L.off_wy + pad16((size_t)(ny - 1) * 4 * es);
     L.gx0 = desc->lut_gx[0];
     L.gy0 = desc->lut_gy[0];
-    L.inv_dx = 1.0 / (desc->lut_gx[1] - desc->lut_gx[0]);
-    L.inv_dy = 1.0 / (desc->lut_gy[1] - desc->lut_gy[0]);
+    L.dx = desc->lut_gx[1] - desc->lut_gx[0];
+    L.dy = desc->lut_gy[1] - desc->lut_gy[0];
+    L.inv_dx = 1.0 / L.dx;
+    L.inv_dy = 1.0 / L.dy;
     std::vector<unsigned char> blob(L.bytes, 0);
     auto put = [&](size_t off, size_t i, double v) {
       if (es == 8)
@@ -516,6 +518,21 @@ int exenv_plan_create(const ExenvDesc *desc, int device, exenv_plan_t *out) {
       delete p;
       return EXENV_ERR_CUDA;
     }
+    if (es == 4 && L.regular && lut_grid_exact_f32(desc->lut_gx, nx) && lut_grid_exact_f32(desc->lut_gy, ny)) {
+      // coefficient form for the fp32 time-major trajectory kernels; used when it fits one CTA's shared memory next to
+      // the schedule buffers (launch_simtm_pmsm_coef_f32 decides)
+      std::vector<float> coef((size_t)(nx - 1) * (ny - 1) * LUT_COEF_STRIDE);
+      lut_coef_fill(desc->lut_maps, nx, ny, coef.data());
+      L.coef_bytes = coef.size() * sizeof(float);
+      if (cudaMalloc(&L.coef, L.coef_bytes) != cudaSuccess ||
+          cudaMemcpy(L.coef, coef.data(), L.coef_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("exenv_plan_create: LUT upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (L.coef) cudaFree(L.coef);
+        cudaFree(L.blob);
+        delete p;
+        return EXENV_ERR_CUDA;
+      }
+    }
     p->desc.lut_gx = p->desc.lut_gy = p->desc.lut_maps = nullptr;  // host pointers are not retained
   }
   *out = p;
@@ -529,6 +546,7 @@ int exenv_plan_destroy(exenv_plan_t plan) {
     DeviceGuard guard(plan->device);  // may run from a garbage collector at any time: leave the current device alone
     for (auto &kv : plan->schedules) free_schedule(kv.second);
     if (plan->lut.blob) cudaFree(plan->lut.blob);
+    if (plan->lut.coef) cudaFree(plan->lut.coef);
     for (int i = 0; i < 3; ++i) {
       if (plan->host_ws[i]) cudaFree(plan->host_ws[i]);
       if (plan->host_stream[i]) cudaStreamDestroy(plan->host_stream[i]);

@@ -23,6 +23,7 @@ struct LutView {
   int nx, ny;
   T inv_dx, inv_dy;  // 1 / grid spacing: only used for the initial cell guess
   T gx0, gy0;        // g[0] of both grids (kernel-argument copies: no read for the arithmetic cell index)
+  T dx, dy;          // grid spacing (coefficient form: cell origins are gx0 + i * dx, exact for the grids it is built for)
   // optional (NULL: plain IEEE division): per grid cell four values {g[i], width d = g[i+1] - g[i], RN(1 / d), 0} -- the
   // cell origin and the operands of the correctly rounded reciprocal division of exenv_math.cuh in one 16-byte read
   const T *wx;
@@ -38,9 +39,14 @@ template <typename T>
 struct LutGeom {
   unsigned bytes, off_gy, off_cells, off_wx, off_wy;
   int nx, ny, regular;
-  T inv_dx, inv_dy, gx0, gy0;
+  T inv_dx, inv_dy, gx0, gy0, dx, dy;
 };
 constexpr int LUT_BLOB_CELL_STRIDE = 7;
+// Coefficient form of the flux maps (fp32 trajectory kernels, Pmsm<float, 2>): per grid CELL the bilinear interpolant of
+// every map as {c0, c_s, c_t, c_st} (value = c0 + s c_s + t (c_t + s c_st), s / t = position inside the cell), six maps
+// = six 16-byte reads instead of 24 four-byte corner reads, 18 FMAs instead of 6 weights + 24 products.  28 words per
+// cell (24 used): with seven 16-byte chunks per cell the chunk index 7 c + q walks through all eight bank groups.
+constexpr int LUT_COEF_STRIDE = 28;
 template <typename T>
 EX_HD LutView<T> lut_view_at(const void *base, const LutGeom<T> &g) {
   const char *b = (const char *)base;
@@ -57,8 +63,53 @@ EX_HD LutView<T> lut_view_at(const void *base, const LutGeom<T> &g) {
   L.inv_dy = g.inv_dy;
   L.gx0 = g.gx0;
   L.gy0 = g.gy0;
+  L.dx = g.dx;
+  L.dy = g.dy;
   L.cs = LUT_BLOB_CELL_STRIDE;
   return L;
+}
+// View over a coefficient-form table (device blob plan.lut.coef / its shared-memory copy): `cells` is the table.
+template <typename T>
+EX_HD LutView<T> lut_view_coef(const void *base, const LutGeom<T> &g) {
+  LutView<T> L{};
+  L.cells = (const T *)base;
+  L.nx = g.nx;
+  L.ny = g.ny;
+  L.regular = 1;
+  L.inv_dx = g.inv_dx;
+  L.inv_dy = g.inv_dy;
+  L.gx0 = g.gx0;
+  L.gy0 = g.gy0;
+  L.dx = g.dx;
+  L.dy = g.dy;
+  L.cs = LUT_COEF_STRIDE;
+  return L;
+}
+// Host: fills the coefficient table from the six maps (map-major, (nx, ny) each, double).  (nx-1) x (ny-1) cells.
+inline void lut_coef_fill(const double *maps, int nx, int ny, float *out) {
+  for (int i = 0; i + 1 < nx; ++i)
+    for (int j = 0; j + 1 < ny; ++j) {
+      float *c = out + ((size_t)i * (ny - 1) + j) * LUT_COEF_STRIDE;
+      for (int q = 0; q < 6; ++q) {
+        const double *m = maps + (size_t)q * nx * ny;
+        const double v00 = m[(size_t)i * ny + j], v01 = m[(size_t)i * ny + j + 1];
+        const double v10 = m[(size_t)(i + 1) * ny + j], v11 = m[(size_t)(i + 1) * ny + j + 1];
+        c[4 * q + 0] = (float)v00;
+        c[4 * q + 1] = (float)(v10 - v00);
+        c[4 * q + 2] = (float)(v01 - v00);
+        c[4 * q + 3] = (float)((v11 - v10) - (v01 - v00));
+      }
+      for (int k = 24; k < LUT_COEF_STRIDE; ++k) c[k] = 0.0f;
+    }
+}
+// Host: the coefficient form needs cell origins that the kernel can rebuild exactly: g[i] == fl(g[0] + i * d) in fp32.
+inline bool lut_grid_exact_f32(const double *g, int n) {
+  if (n < 2) return false;
+  const float g0 = (float)g[0], d = (float)(g[1] - g[0]);
+  if (!(d > 0.0f) || (double)g0 != g[0] || (double)d != g[1] - g[0]) return false;
+  for (int i = 0; i < n; ++i)
+    if ((double)(g0 + (float)i * d) != g[i] || (double)((float)i * d) != (double)i * (double)d) return false;
+  return true;
 }
 
 // searchsorted(g, x, side="left") - 1 clipped to [0, n-2]  (jax RegularGridInterpolator._find_indices)
@@ -145,6 +196,35 @@ EX_HD void lut_eval_direct(const LutView<T> &L, T id, T iq, T *out) {
     v = fma_(c10[L.cs + FIRST + q], w11, v);
     out[q] = v;
   }
+}
+// Coefficient-form look-up (LutView from lut_view_coef).  Cell by arithmetic as above; the position inside the cell from
+// the exactly rebuilt cell origin (lut_grid_exact_f32), times the reciprocal spacing; outside the grid the edge cell
+// extrapolates linearly, like the four-corner form with weights outside [0, 1] (RegularGridInterpolator, fill_value=None).
+template <typename T, int FIRST, int COUNT>
+EX_HD void lut_eval_coef(const LutView<T> &L, T id, T iq, T *out) {
+  const T fi = min_(max_((id - L.gx0) * L.inv_dx, (T)0), (T)(L.nx - 2));
+  const T fj = min_(max_((iq - L.gy0) * L.inv_dy, (T)0), (T)(L.ny - 2));
+  const int i = (int)fi, j = (int)fj;  // truncation; NaN -> 0 (fmax / fmin drop a NaN)
+  const T s = (id - fma_((T)i, L.dx, L.gx0)) * L.inv_dx;
+  const T t = (iq - fma_((T)j, L.dy, L.gy0)) * L.inv_dy;
+  const T *c = L.cells + (i * (L.ny - 1) + j) * LUT_COEF_STRIDE + 4 * FIRST;
+#if defined(__CUDA_ARCH__)
+  // all COUNT reads are issued before the first result is used: one shared-memory latency per look-up.  Left to itself
+  // ptxas recycles one or two register quads and pays the latency per map -- a third of the kernel's stall samples
+  // (profiles/README.md).  The warp-level barrier is the fence it does not move shared-memory reads across; it orders
+  // nothing the kernel needs ordered.  All 32 lanes arrive: the trajectory kernel that instantiates Pmsm<float, 2> keeps
+  // every lane of a running warp in its loops (surplus lanes shadow the last environment).
+  float4 k[COUNT];
+#pragma unroll
+  for (int q = 0; q < COUNT; ++q) k[q] = *reinterpret_cast<const float4 *>(c + 4 * q);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < COUNT; ++q) out[q] = fma_(t, fma_(s, (T)k[q].w, (T)k[q].z), fma_(s, (T)k[q].y, (T)k[q].x));
+#else
+#pragma unroll
+  for (int q = 0; q < COUNT; ++q)
+    out[q] = fma_(t, fma_(s, c[4 * q + 3], c[4 * q + 2]), fma_(s, c[4 * q + 1], c[4 * q]));
+#endif
 }
 struct NoAux {};
 
@@ -434,11 +514,12 @@ struct env_packable<Acrobot<float>> {
 // ---- PMSM (pmsm/pmsm_env.py) -----------------------------------------------------------------------------------
 // PhysicalState fields: 0 u_d_buffer, 1 u_q_buffer, 2 epsilon, 3 i_d, 4 i_q, 5 torque, 6 omega_el (:281-291)
 // ODE state y = (i_d, i_q, epsilon) (:555).  p = p, r_s, l_d, l_q, psi_p, u_dc, deadtime.
-template <typename T, bool SAT>
+template <typename T, int SAT>  // 0 linear, 1 saturated (flux-map nodes), 2 saturated, coefficient-form maps (fp32)
 struct Pmsm {
   static constexpr int ID = 5, D = 7, NODE = 3, A = 2, O = 8, NSTATIC = 7, NTRUNC_BASE = 1;
   static constexpr bool IS_PMSM = true;
-  static constexpr bool SATURATED = SAT;
+  static constexpr bool SATURATED = SAT != 0;
+  static constexpr bool COEF = SAT == 2;
   using Aux = PmsmAux<T>;
 
   struct Pre {
@@ -458,6 +539,34 @@ struct Pmsm {
       const T l_d = p[2], l_q = p[3], psi_p = p[4];
       dy[0] = div_inv<FAST, T>(u[0] + w * l_q * iq - r_s * id, q_.ld);
       dy[1] = div_inv<FAST, T>(u[1] - w * (l_d * id + psi_p) - r_s * iq, q_.lq);
+    } else if constexpr (COEF) {  // :487-507 nonlinear_ode with coefficient-form maps: the solve of the FAST branch
+                                  // below; the row exchange of the partial pivoting behind ONE warp vote (the direct
+                                  // inductances dominate the cross terms by > 10x on every shipped map: no lane ever
+                                  // exchanges, and the common case runs without the seven selects)
+      T q[6];
+      lut_eval_coef<T, 0, 6>(aux.lut, id, iq, q);
+      const T rhs0 = fma_(w, q[5], fma_(-r_s, id, u[0]));
+      const T rhs1 = fma_(-w, q[4], fma_(-r_s, iq, u[1]));
+      const bool swap = Mth<T>::abs(q[2]) > Mth<T>::abs(q[0]);
+#if defined(__CUDA_ARCH__)
+      if (!__any_sync(0xffffffffu, swap)) {  // all 32 lanes are here, see lut_eval_coef
+        const T i00 = rcp_nr(q[0]);
+        const T lf = q[2] * i00;
+        const T x1 = fma_(-lf, rhs0, rhs1) * rcp_nr(fma_(-lf, q[1], q[3]));
+        dy[0] = fma_(-q[1], x1, rhs0) * i00;
+        dy[1] = x1;
+      } else
+#endif
+      {
+        const T b00 = swap ? q[2] : q[0], b01 = swap ? q[3] : q[1];
+        const T b10 = swap ? q[0] : q[2], b11 = swap ? q[1] : q[3];
+        const T r0 = swap ? rhs1 : rhs0, r1 = swap ? rhs0 : rhs1;
+        const T i00 = rcp_nr(b00);
+        const T lf = b10 * i00;
+        const T x1 = fma_(-lf, r0, r1) * rcp_nr(fma_(-lf, b01, b11));
+        dy[0] = fma_(-b01, x1, r0) * i00;
+        dy[1] = x1;
+      }
     } else if constexpr (FAST && sizeof(T) == 4) {  // :487-507 nonlinear_ode, instruction-bound fp32 kernels (fp64 keeps
                                                     // the reference's order of operations: its per-step tolerance is 1e-12)
       // Look-up (lut_eval_direct); then, instead of forming inv(L) (LU with partial pivoting + two solves) and three
@@ -518,7 +627,8 @@ struct Pmsm {
       return (T)1.5 * p[0] * (p[4] + (p[2] - p[3]) * id) * iq;
     } else {
       T q[2];
-      if constexpr (FAST && sizeof(T) == 4) lut_eval_direct<T, 4, 2>(aux.lut, id, iq, q);
+      if constexpr (COEF) lut_eval_coef<T, 4, 2>(aux.lut, id, iq, q);
+      else if constexpr (FAST && sizeof(T) == 4) lut_eval_direct<T, 4, 2>(aux.lut, id, iq, q);
       else lut_eval<T, 4, 2>(aux.lut, id, iq, q);
       return (T)1.5 * p[0] * (q[0] * iq - q[1] * id);
     }

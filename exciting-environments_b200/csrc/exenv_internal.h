@@ -51,7 +51,11 @@ struct DevLut {
   size_t bytes = 0, off_gy = 0, off_cells = 0, off_wx = 0, off_wy = 0;
   int nx = 0, ny = 0;
   int regular = 0;       // both grids equidistant up to rounding (cell guess at most one off)
-  double inv_dx = 0, inv_dy = 0, gx0 = 0, gy0 = 0;
+  double inv_dx = 0, inv_dy = 0, gx0 = 0, gy0 = 0, dx = 0, dy = 0;
+  // fp32 plans whose grids are equidistant with exactly representable nodes: the coefficient form of the maps
+  // (exenv_envs.cuh: LUT_COEF_STRIDE words per cell), read by the time-major trajectory kernels of Pmsm<float, 2>
+  void *coef = nullptr;
+  size_t coef_bytes = 0;
 };
 
 }  // namespace exenv
@@ -91,6 +95,8 @@ int launch_sim_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedu
 int launch_sim_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
+// saturated PMSM, Tsit5, coefficient-form flux maps (exenv_simtm_pmsm_coef_f32.cu); plan.lut.coef must exist
+int launch_simtm_pmsm_coef_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_packed_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream,
                             int envs_per_thread);
 size_t sim_smem_bytes_f32(const ExenvPlan &plan, int step_cap, int act_cap, int save_cap);

@@ -48,6 +48,8 @@ inline LutGeom<T> make_lut_geom(const ExenvPlan &plan) {
   g.inv_dy = (T)plan.lut.inv_dy;
   g.gx0 = (T)plan.lut.gx0;
   g.gy0 = (T)plan.lut.gy0;
+  g.dx = (T)plan.lut.dx;
+  g.dy = (T)plan.lut.dy;
   return g;
 }
 template <typename T>

@@ -25,8 +25,33 @@
 
 namespace exenv {
 
+// Multiprocessors of a device (grid size of the persistent flavour), queried once per device.
+static int device_sm_count(int device) {
+  static std::mutex mu;
+  static int cache[64] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  int &n = cache[device & 63];
+  if (n <= 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) n = 148;
+  return n > 0 ? n : 148;
+}
+
+// EXENV_PMSM_COEF=0 keeps the node-form flux maps in the saturated-PMSM fp32 trajectory kernels (A/B measurements).
+static bool simtm_coef_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("EXENV_PMSM_COEF");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+// Whether launch_simtm_pmsm_coef_f32 can run this plan: coefficient table built (fp32, exact equidistant grids) and
+// table + mbarrier + schedule buffers of the persistent CTA within the 227 KB of one CTA.
+static bool simtm_coef_fits(const ExenvPlan &plan) {
+  return plan.lut.coef && simtm_coef_enabled() &&
+         ((plan.lut.coef_bytes + 16 + 15) & ~(size_t)15) + tm_sched_smem_bytes<float>(SIMTM_COEF_THREADS) <= 227 * 1024;
+}
+
 template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
-__global__ void __launch_bounds__(SIMTM_THREADS)
+__global__ void __launch_bounds__(simtm_cta_threads<Env>())
     simtm_kernel(const __grid_constant__ SimTmK<T> a, const __grid_constant__ KParams<T> kp,
                  const __grid_constant__ SimTmHostPre<Env, T> hp) {
   constexpr int D = Env::D, A = Env::A, NODE = Env::NODE, O = Env::O, NP = num_params<Env>();
@@ -38,9 +63,11 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   // First environment of this thread.  A warp entirely beyond the batch leaves; in the warp that straddles its end the
   // surplus lanes shadow the last group of V environments (same loads, same arithmetic, same values stored to the same
   // addresses): every warp that runs the loop runs it with all 32 lanes, which the shared-memory schedule staging needs.
-  const long b_own = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;
-  const bool valid = b_own - (long)(threadIdx.x & 31) * V < a.B;
-  const long b = b_own < a.B ? b_own : a.B - V;
+  // A job = the 32 * V consecutive environments of one warp.  One job per warp, CTA-major -- or, for the persistent
+  // coefficient-form PMSM flavour, a strided sequence of jobs per warp (exenv_simtm_common.cuh: simtm_is_coef).
+  constexpr bool PERSIST = simtm_is_coef<Env>();
+  const unsigned lane = threadIdx.x & 31u, warp_in_cta = threadIdx.x >> 5;
+  long job = PERSIST ? (long)warp_in_cta * gridDim.x + blockIdx.x : (long)blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
 
   typename Env::Aux aux[V];
   // dynamic shared memory: [PMSM flux maps + mbarrier (saturated only) | per-warp schedule buffers]
@@ -70,10 +97,15 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      aux[v].lut = lut_view_at<T>(sm_lut, a.lut);
+      if constexpr (PERSIST) aux[v].lut = lut_view_coef<T>(sm_lut, a.lut);
+      else aux[v].lut = lut_view_at<T>(sm_lut, a.lut);
     }
   }
-  if (!valid) return;  // no block-wide synchronisation below
+  // no block-wide synchronisation below
+  for (;; job += (long)(blockDim.x >> 5) * gridDim.x) {
+  if (job * (32 * V) >= a.B) return;
+  const long b_own = (job * 32 + lane) * V;
+  const long b = b_own < a.B ? b_own : a.B - V;
 
   // ---- per-environment constants and initial state ------------------------------------------------------------
   T pl[NP];
@@ -214,14 +246,12 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   // leaf and per observation row group, through running row pointers.  Further saves of the same step and the
   // GENERIC instantiation store element-wise.
   const unsigned Bu = (unsigned)a.B;
-  T *tp[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) tp[d] = a.traj[d] ? a.traj[d] + b : nullptr;
-  T *op = a.obs + b * OW;
+  // ONE running element index addresses every output of the fast path: (save step_first_save, environment b) of an
+  // (N+1, B) array; leaf / observation / flag addresses are formed from the kernel-argument base pointers at the store
+  // (the same two integer instructions a running pointer per array would spend on its increment, and 2 (D + 3) fewer
+  // live registers).  reward / terminated rows are those of states[1:]: one row behind.
+  size_t srow = (size_t)b;
   constexpr int NT0 = trunc_dim<Env>(0);  // truncated width without reference entries
-  T *rwp = EPI ? a.reward + b : nullptr;  // rows of states[1:]: they start moving after save 0
-  uint8_t *trp = EPI ? a.trunc + b * NT0 : nullptr;
-  uint8_t *tmp = EPI ? a.term + b : nullptr;
   auto flags_fast = [&](const T *sv, const T *, uint8_t *tr, uint8_t &te) {  // control_state == []
     bool t0 = false;
 #pragma unroll
@@ -252,30 +282,31 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
     }
   };
   auto sink_v = [&](int v, long sidx, const T *st) {
+    if constexpr (GENERIC) {  // (the fast path reads last_state back from the trajectory rows it has written)
 #pragma unroll
-    for (int i = 0; i < NST; ++i) last[v][i] = st[i];
+      for (int i = 0; i < NST; ++i) last[v][i] = st[i];
+    }
     if constexpr (!GENERIC) {
       if (sidx == step_first_save) {
 #pragma unroll
         for (int i = 0; i < NST; ++i) stash[v][i] = st[i];
       } else {  // rare: a later save of the same step
-        const size_t roff = (size_t)(sidx - step_first_save) * Bu + v;
+        const size_t row = srow + (size_t)(sidx - step_first_save) * Bu + v;
         T sv[D], ob[O];
         staged_to_fields<Env, T>(st, s0[v][D - 1], sv);
 #pragma unroll
-        for (int d = 0; d < D; ++d) __stcs(tp[d] + roff, sv[d]);
+        for (int d = 0; d < D; ++d) __stcs(a.traj[d] + row, sv[d]);
         obs_fast(v, st, sv, ob);
 #pragma unroll
-        for (int o = 0; o < O; ++o) __stcs(op + roff * O + o, ob[o]);
+        for (int o = 0; o < O; ++o) __stcs(a.obs + row * O + o, ob[o]);
         if constexpr (EPI) {
           uint8_t tr[NT0], te;
           flags_fast(sv, ob, tr, te);
 #pragma unroll
-          for (int i = 0; i < NT0; ++i) trp[roff * NT0 + i] = tr[i];
+          for (int i = 0; i < NT0; ++i) a.trunc[row * NT0 + i] = tr[i];
           // reward / terminated rows run one save behind (states[1:]); sidx > step_first_save >= 0 here
-          const size_t r1 = (size_t)(sidx - step_first_save - (step_first_save == 0 ? 1 : 0)) * Bu + v;
-          __stcs(rwp + r1, (T)0);
-          tmp[r1] = te;
+          __stcs(a.reward + (row - Bu), (T)0);
+          a.term[row - Bu] = te;
         }
       }
     } else {
@@ -329,11 +360,9 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
         T col[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) col[v] = sv[v][d];
-        store_vec<T, V>(tp[d], col);
-        tp[d] += (size_t)Bu * (unsigned)ns;
+        store_vec<T, V>(a.traj[d] + srow, col);
       }
-      store_vec<T, V * O>(op, &ob[0][0]);
-      op += (size_t)Bu * (unsigned)(ns * O);
+      store_vec<T, V * O>(a.obs + srow * O, &ob[0][0]);
       if constexpr (EPI) {
         uint8_t tr[V][NT0], te[V];
         T zero[V];
@@ -342,16 +371,13 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
           flags_fast(sv[v], ob[v], tr[v], te[v]);
           zero[v] = (T)0;
         }
-        store_vec<uint8_t, V * NT0>(trp, &tr[0][0]);
-        trp += (size_t)Bu * (unsigned)(ns * NT0);
+        store_vec<uint8_t, V * NT0>(a.trunc + srow * NT0, &tr[0][0]);
         if (step_first_save > 0) {  // save 0 has no reward / terminated entry
-          store_vec<T, V>(rwp, zero);
-          store_vec<uint8_t, V>(tmp, te);
+          store_vec<T, V>(a.reward + (srow - Bu), zero);
+          store_vec<uint8_t, V>(a.term + (srow - Bu), te);
         }
-        const unsigned adv = (unsigned)(step_first_save > 0 ? ns : ns - 1);
-        rwp += (size_t)Bu * adv;
-        tmp += (size_t)Bu * adv;
       }
+      srow += (size_t)Bu * (unsigned)ns;
     }
   };
 
@@ -416,20 +442,29 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
   if (want_k && q_last > wbase + W - 1) slide_to(q_last - (W - 1));
   (void)pend_valid;
   T sl[V][D], fi[V][NODE];
+  if constexpr (!GENERIC) {  // the fields of the last save, as this thread has just written them
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      T col[V];
+      load_vec<T, V>(col, a.traj[d] + ((size_t)(a.n_save - 1) * Bu + (size_t)b));
+#pragma unroll
+      for (int v = 0; v < V; ++v) sl[v][d] = col[v];
+    }
+  }
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    staged_to_fields<Env, T>(last[v], s0[v][D - 1], sl[v]);
+    if constexpr (GENERIC) staged_to_fields<Env, T>(last[v], s0[v][D - 1], sl[v]);
     if (want_k) {
       // solver.init(term, t1, t1 + tau, y_last, args): derivative with the ZOH closure at t1 -> clamped last action
       T u[A], yl[NODE];
       win[v](q_last, u);
-      if constexpr (Env::IS_PMSM) {
-        yl[0] = last[v][1];
-        yl[1] = last[v][2];
-        yl[2] = last[v][0];
+      if constexpr (Env::IS_PMSM) {  // ODE state (i_d, i_q, epsilon) = fields 3, 4, 2
+        yl[0] = sl[v][3];
+        yl[1] = sl[v][4];
+        yl[2] = sl[v][2];
       } else {
 #pragma unroll
-        for (int i = 0; i < NODE; ++i) yl[i] = last[v][i];
+        for (int i = 0; i < NODE; ++i) yl[i] = sl[v][i];
       }
       sim_rhs<Env, T>(yl, u, p, pre, aux[v], fi[v]);
     }
@@ -451,15 +486,22 @@ __global__ void __launch_bounds__(SIMTM_THREADS)
       store_vec<T, V>(a.klast[i] + b, col);
     }
   }
+  if constexpr (!PERSIST) return;
+  }  // next job of this warp
 }
 
 template <class Env, int SOLVER, typename T, bool PER_ENV, bool GENERIC, int W, int V, bool EPI>
 static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const SimSchedule &sch, cudaStream_t stream) {
-  const SimTmK<T> a = simtm_args<Env, T>(plan, x, sch);
+  SimTmK<T> a = simtm_args<Env, T>(plan, x, sch);
   KParams<T> kp = make_kparams<T>(plan);
+  constexpr bool COEF = simtm_is_coef<Env>();
+  if constexpr (COEF) {  // the kernel stages the coefficient-form table instead of the node blob
+    a.lut_blob = plan.lut.coef;
+    a.lut.bytes = (unsigned)plan.lut.coef_bytes;
+  }
   size_t smem = 0;
-  if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = (plan.lut.bytes + 16 + 15) & ~(size_t)15;
-  smem += tm_sched_smem_bytes<T>(SIMTM_THREADS);
+  if (Env::IS_PMSM && (plan.desc.flags & EXENV_FLAG_SATURATED)) smem = ((size_t)a.lut.bytes + 16 + 15) & ~(size_t)15;
+  smem += tm_sched_smem_bytes<T>(simtm_cta_threads<Env>());
   auto kern = simtm_kernel<Env, SOLVER, T, PER_ENV, GENERIC, W, V, EPI>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -469,8 +511,9 @@ static int launch_simtm_v(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
     }
   }
   const long threads = (x.batch + V - 1) / V;
-  const int nthr = simtm_block_threads();
-  const unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
+  const int nthr = COEF ? SIMTM_COEF_THREADS : simtm_block_threads();
+  unsigned grid = (unsigned)((threads + nthr - 1) / nthr);
+  if (COEF) grid = std::min<unsigned>(grid, (unsigned)device_sm_count(plan.device));  // persistent: one CTA per SM
   bool thr_ok = true;
   const SimTmHostPre<Env, T> hp = make_host_pre<Env, T>(kp, EPI ? &thr_ok : nullptr);
   if (!thr_ok) {
@@ -595,6 +638,11 @@ static int simtm_dispatch2(const ExenvPlan &plan, const ExenvSimArgs &x, const S
   if (generic)
     return tsit ? launch_simtm_w<Env, EXENV_TSIT5, T, false, true, 1>(plan, x, s, st)
                 : launch_simtm_w<Env, EXENV_EULER, T, false, true, 1>(plan, x, s, st);
+#if !defined(EXENV_SIMTM_COEF_TU)
+  if constexpr (Env::IS_PMSM && Env::SATURATED && std::is_same<T, float>::value) {
+    if (tsit && simtm_coef_fits(plan)) return launch_simtm_pmsm_coef_f32(plan, x, s, st);  // exenv_simtm_pmsm_coef_f32.cu
+  }
+#endif
   return tsit ? launch_simtm_fast<Env, EXENV_TSIT5, T>(plan, x, s, st) : launch_simtm_fast<Env, EXENV_EULER, T>(plan, x, s, st);
 }
 
@@ -614,9 +662,16 @@ static int simtm_dispatch(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
   return EXENV_ERR_INVALID;
 }
 
+#if defined(EXENV_SIMTM_COEF_TU)
+// Tsit5 trajectories of the saturated PMSM with coefficient-form flux maps, with and without the fused epilogue
+int launch_simtm_pmsm_coef_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream) {
+  return launch_simtm_fast<Pmsm<float, 2>, EXENV_TSIT5, float>(plan, a, sch, stream);
+}
+#else
 int EXENV_CAT(launch_simtm_, EXENV_SFX)(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch,
                                          cudaStream_t stream) {
   return simtm_dispatch<EXENV_REAL>(plan, a, sch, stream);
 }
+#endif
 
 }  // namespace exenv

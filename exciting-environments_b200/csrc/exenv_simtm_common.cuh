@@ -29,6 +29,27 @@ static int simtm_block_threads() {
   return n;
 }
 
+// Saturated PMSM with coefficient-form flux maps (Pmsm<float, 2>): the table of a whole motor (BRUSA: 157 KB) fits one
+// CTA's shared memory once per SM, so that flavour runs ONE persistent CTA per SM and hands whole warps their
+// environments: warp w of CTA c takes the 32-environment jobs w * gridDim.x + c, + warps * gridDim.x, ... (warp-major,
+// so that the jobs of a partially filled last round are spread over all SMs: an SM whose later warps have retired runs
+// the others faster, as with the small CTAs of the other flavours).
+// 512 threads = 16 warps at <= 128 registers (the kernel needs 113-119 once the six reads of a look-up are fenced,
+// exenv_envs.cuh: lut_eval_coef).
+template <class Env>
+constexpr bool simtm_is_coef() {
+  if constexpr (Env::IS_PMSM) return Env::COEF;
+  else return false;
+}
+#ifndef EXENV_COEF_THREADS
+#define EXENV_COEF_THREADS 512
+#endif
+constexpr int SIMTM_COEF_THREADS = EXENV_COEF_THREADS;
+template <class Env>
+constexpr int simtm_cta_threads() {
+  return simtm_is_coef<Env>() ? SIMTM_COEF_THREADS : SIMTM_THREADS;
+}
+
 template <typename T>
 struct SimTmK {
   long B, n_actions, n_save, n_steps;
@@ -159,6 +180,10 @@ struct TmSchedReader {
   __device__ __forceinline__ void init(const TmStep<T> *records, unsigned char *smem_base) {
     g = records;
     buf = reinterpret_cast<TmStep<T> *>(smem_base) + (size_t)(threadIdx.x >> 5) * 2 * TM_CHUNK;
+    // a persistent warp starting its next job: the look-ahead copy of the previous one has landed and every lane is done
+    // reading the buffers
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     stage(0);
     enter_chunk(0);
   }

@@ -188,6 +188,52 @@ void hc_sincos2(long n, const float *x, float *s, float *c) {
     c[i + 1] = cs.y;
   }
 }
+// exenv_envs.cuh: the saturated-PMSM look-up in its node form (four corners) and its coefficient form (Pmsm<float, 2>),
+// and the right-hand side built on each.  maps: (6, nx, ny) doubles; points (id, iq); out_*: (n, 6); dy_*: (n, 3).
+// Returns whether both grids qualify for the coefficient form (lut_grid_exact_f32).
+int hc_lut_forms(long n, const double *gx, const double *gy, const double *maps, int nx, int ny, const float *id,
+                 const float *iq, const float *u, const float *omega, const float *params, float *out_node,
+                 float *out_coef, float *dy_node, float *dy_coef) {
+  std::vector<float> gxf(gx, gx + nx), gyf(gy, gy + ny), cells((size_t)nx * ny * 6);
+  for (int q = 0; q < 6; ++q)
+    for (int i = 0; i < nx; ++i)
+      for (int j = 0; j < ny; ++j) cells[((size_t)i * ny + j) * 6 + q] = (float)maps[((size_t)q * nx + i) * ny + j];
+  LutView<float> node{};
+  node.gx = gxf.data();
+  node.gy = gyf.data();
+  node.cells = cells.data();
+  node.nx = nx;
+  node.ny = ny;
+  node.inv_dx = (float)(1.0 / (gx[1] - gx[0]));
+  node.inv_dy = (float)(1.0 / (gy[1] - gy[0]));
+  node.regular = 1;
+  node.cs = 6;
+  const bool exact = lut_grid_exact_f32(gx, nx) && lut_grid_exact_f32(gy, ny);
+  std::vector<float> coef((size_t)(nx - 1) * (ny - 1) * LUT_COEF_STRIDE);
+  lut_coef_fill(maps, nx, ny, coef.data());
+  LutGeom<float> g{};
+  g.nx = nx;
+  g.ny = ny;
+  g.gx0 = (float)gx[0];
+  g.gy0 = (float)gy[0];
+  g.dx = (float)(gx[1] - gx[0]);
+  g.dy = (float)(gy[1] - gy[0]);
+  g.inv_dx = node.inv_dx;
+  g.inv_dy = node.inv_dy;
+  const LutView<float> cv = lut_view_coef<float>(coef.data(), g);
+  for (long k = 0; k < n; ++k) {
+    lut_eval<float, 0, 6>(node, id[k], iq[k], out_node + 6 * k);
+    lut_eval_coef<float, 0, 6>(cv, id[k], iq[k], out_coef + 6 * k);
+    const float y[3] = {id[k], iq[k], 0.0f};
+    PmsmAux<float> a1{}, a2{};
+    a1.omega_el = a2.omega_el = omega[k];
+    a1.lut = node;
+    a2.lut = cv;
+    Pmsm<float, 1>::rhs<true>(y, u + 2 * k, params, Pmsm<float, 1>::precompute(params), a1, dy_node + 3 * k);
+    Pmsm<float, 2>::rhs<true>(y, u + 2 * k, params, Pmsm<float, 2>::precompute(params), a2, dy_coef + 3 * k);
+  }
+  return exact ? 1 : 0;
+}
 void hc_fmod_two_pi(long n, int is_f64, const void *x, void *fmod_out, void *wrap_out) {
   for (long i = 0; i < n; ++i) {
     if (is_f64) {

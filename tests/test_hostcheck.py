@@ -239,3 +239,72 @@ def test_packed_sincos_accuracy(hostcheck_lib):
     with np.errstate(invalid="ignore"):
         assert np.allclose(sb, np.sin(big.astype(np.float64)), rtol=0, atol=2e-7, equal_nan=True)
         assert np.allclose(cb, np.cos(big.astype(np.float64)), rtol=0, atol=2e-7, equal_nan=True)
+
+
+@pytest.mark.parametrize("motor", ["BRUSA", "SEW"])
+def test_flux_map_coefficient_form(hostcheck_lib, motor):
+    """exenv_envs.cuh: lut_eval_coef / Pmsm<float, 2> -- the coefficient form of the saturated-PMSM flux maps that the
+    fp32 time-major trajectory kernel reads (one 16-byte read per map and cell).  Against the bilinear interpolant in
+    float64 (RegularGridInterpolator semantics incl. linear extrapolation outside the grid, pmsm_env.py:352-361) it is
+    as close as the four-corner form of the reference evaluated in float32, and so is the right-hand side built on it
+    (pmsm_env.py:487-507)."""
+    from scipy.interpolate import RegularGridInterpolator
+
+    gx, gy, maps = O.load_motor_lut(motor)
+    nx, ny = gx.size, gy.size
+    rng = np.random.default_rng(5)
+    n = 200000
+    lo = np.array([gx[0], gy[0]]) - 2 * (gx[1] - gx[0])
+    hi = np.array([gx[-1], gy[-1]]) + 2 * (gx[1] - gx[0])
+    pts = rng.uniform(lo, hi, (n, 2))
+    # grid nodes, points a rounding error away from grid lines and far outside
+    k = 2000
+    pts[:k, 0] = rng.choice(gx, k) + rng.choice([0.0, 1e-5, -1e-5], k)
+    pts[k:2 * k, 1] = rng.choice(gy, k) + rng.choice([0.0, 1e-5, -1e-5], k)
+    pts[2 * k:2 * k + 100] *= 3.0
+    idq = pts.astype(np.float32)
+    i_d, i_q = np.ascontiguousarray(idq[:, 0]), np.ascontiguousarray(idq[:, 1])
+    orc = O.Oracle("pmsm", solver=O.TSIT5, dtype=np.float32, saturated=True, motor=motor)
+    params = np.ascontiguousarray(np.array([orc.desc.p[i] for i in range(32)], np.float32))
+    u = rng.uniform(-200, 200, (n, 2)).astype(np.float32)
+    om = rng.uniform(-3000, 3000, n).astype(np.float32)
+    node, coef = np.empty((n, 6), np.float32), np.empty((n, 6), np.float32)
+    dyn, dyc = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+    mp = np.ascontiguousarray(maps, np.float64)
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    hostcheck_lib.hc_lut_forms.restype = C.c_int
+    exact = hostcheck_lib.hc_lut_forms(C.c_long(n), P(np.ascontiguousarray(gx)), P(np.ascontiguousarray(gy)), P(mp),
+                                       C.c_int(nx), C.c_int(ny), P(i_d), P(i_q), P(u), P(om), P(params), P(node), P(coef),
+                                       P(dyn), P(dyc))
+    assert exact == 1  # the shipped motors' grids are integer-valued and equidistant
+    x64 = idq.astype(np.float64)
+    truth = np.stack([RegularGridInterpolator((gx, gy), maps[q], method="linear", bounds_error=False, fill_value=None)(x64)
+                      for q in range(6)], axis=1)
+    scale = np.abs(maps).reshape(6, -1).max(axis=1)
+    inside = (np.abs(x64[:, 0] - (gx[0] + gx[-1]) / 2) <= (gx[-1] - gx[0]) / 2) & \
+             (np.abs(x64[:, 1] - (gy[0] + gy[-1]) / 2) <= (gy[-1] - gy[0]) / 2)
+    e_node = np.abs(node - truth) / scale
+    e_coef = np.abs(coef - truth) / scale
+    # inside the grid: a few float32 ulp of the map's range (random points: 1.4e-7 against 2.1e-7 for the four-corner
+    # form; worst at the far edge of a cell of the small cross-inductance maps, where the increments cancel: 6e-7);
+    # outside the extrapolated value grows with the distance
+    assert e_coef[inside].max() <= 1e-6, e_coef[inside].max()
+    assert e_coef[inside].max() <= 4 * e_node[inside].max() + 1e-7
+    assert e_coef[inside].mean() <= e_node[inside].mean()
+    grow = 1.0 + np.abs(truth) / scale
+    assert (e_coef / grow).max() <= 1e-6  # (the four-corner weights cancel far outside: up to 1e-4 there)
+    # right-hand side in float64 from the float64 look-up: inv(L) (u - r_s i - omega J Psi)
+    r_s = float(params[1])
+    L = truth[:, :4].reshape(n, 2, 2)
+    psi = truth[:, 4:6]
+    b = u.astype(np.float64) - r_s * x64 - om[:, None].astype(np.float64) * np.stack([-psi[:, 1], psi[:, 0]], axis=1)
+    want = np.linalg.solve(L, b[:, :, None])[:, :, 0]
+    # error scale: the terms of the right-hand side before they cancel, through the inverse
+    terms = np.abs(u.astype(np.float64)) + r_s * np.abs(x64) + np.abs(om[:, None].astype(np.float64)) * np.abs(psi[:, ::-1])
+    scl = (np.linalg.norm(np.linalg.inv(L), 2, axis=(1, 2)) * terms.max(axis=1))[:, None]
+    en = (np.abs(dyn[:, :2] - want) / scl)[inside]
+    ec = (np.abs(dyc[:, :2] - want) / scl)[inside]
+    print("rhs error / scale: node", en.max(), "coef", ec.max())
+    assert ec.max() <= 1e-6, ec.max()
+    assert ec.max() <= 4 * en.max() + 1e-7, (ec.max(), en.max())
+    assert np.array_equal(dyc[:, 2], om) and np.array_equal(dyn[:, 2], om)
