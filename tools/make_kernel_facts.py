@@ -12,9 +12,9 @@ P = Path(__file__).resolve().parent.parent / "profiles"
 # key: (summary file, envs, steps per launch, profile_one.py arguments)
 ROWS = {
     "simtm_msd_tsit5_f32": ("r02_simtm_packed_kernel_msd_tsit5_f32.txt", 524288, 1000, "sim msd tsit5 f32 524288 1000 0 4 tm"),
-    "simtm_pmsm_sat_tsit5_f32_epi": ("r02_simtm_kernel_pmsm_sat_tsit5_f32_epi_gentle.txt", 131072, 500,
+    "simtm_pmsm_sat_tsit5_f32_epi": ("r02_simtm_kernel_pmsm_sat_coef_tsit5_f32_epi_gentle.txt", 131072, 500,
                                      "EXENV_PROFILE_ACT_SCALE=0.02 sim pmsm_sat tsit5 f32 131072 500 0 0 tm epi"),
-    "simtm_pmsm_sat_tsit5_f32_epi_full_range": ("r02_simtm_kernel_pmsm_sat_tsit5_f32_epi.txt", 131072, 500,
+    "simtm_pmsm_sat_tsit5_f32_epi_full_range": ("r02_simtm_kernel_pmsm_sat_coef_tsit5_f32_epi.txt", 131072, 500,
                                                 "sim pmsm_sat tsit5 f32 131072 500 0 0 tm epi"),
     "simtm_pendulum_euler_f32": ("r02_simtm_packed_kernel_pendulum_euler_f32.txt", 1048576, 1000,
                                  "sim pendulum euler f32 1048576 1000 0 0 tm"),
