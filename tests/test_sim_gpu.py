@@ -458,6 +458,49 @@ def test_config4_pmsm_saturated_full_horizon_properties(excenvs):
         assert ((a - b).abs().max() / scales[name]).item() < 1e-3, name
 
 
+@pytest.mark.parametrize("motor", ["brusa", "sew"])
+def test_persistent_pmsm_kernel_job_mapping(excenvs, motor):
+    """The coefficient-form saturated-PMSM kernel (Pmsm<float, 2>) runs one persistent 512-thread CTA per SM whose warps
+    walk 32-environment jobs (exenv_simtm_common.cuh).  A ragged batch of more than one round (148 SMs x 512 threads):
+    some warps run two jobs, the last job is partial.  Every environment must get the trajectory the same inputs get
+    in a small batch (a different job, warp and CTA: bit-identical), a sample of them is compared with the oracle,
+    and the fused flags equal their definition on the returned states."""
+    import torch.cuda
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, T = sms * 512 + 5 * 32 + 13, 24
+    orc = _orc(f"pmsm_{motor}_sat", O.TSIT5, np.float32)
+    rng = np.random.default_rng(17)
+    st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=True)
+    acts = (rng.uniform(-1, 1, (B, T, 2)) * 0.02).astype(np.float32)
+    e = make_env(excenvs, orc, B)
+    a_dev = torch.as_tensor(acts, device="cuda")
+    obs, states, last, rew, trunc, term = e.vmap_sim_ahead_with_epilogue(to_state(e, st), a_dev, orc.tau, orc.tau,
+                                                                         layout="time_major")
+    # the same environments in a small batch, in another order of jobs
+    pick = np.concatenate([np.arange(0, 64), np.arange(B - 77, B), rng.choice(B, 500, replace=False)])
+    sub = [x[pick] for x in st]
+    e2 = make_env(excenvs, orc, pick.size)
+    obs2, states2, last2, rew2, trunc2, term2 = e2.vmap_sim_ahead_with_epilogue(
+        to_state(e2, sub), torch.as_tensor(acts[pick], device="cuda"), orc.tau, orc.tau, layout="time_major")
+    idx = torch.as_tensor(pick, device="cuda")
+    assert torch.equal(obs[idx], obs2) and torch.equal(trunc[idx], trunc2) and torch.equal(term[idx], term2)
+    for n in e.PHYS_FIELDS:
+        assert torch.equal(getattr(states.physical_state, n)[idx], getattr(states2.physical_state, n)), n
+        assert torch.equal(getattr(last.physical_state, n)[idx], getattr(last2.physical_state, n)), n
+    for a, b in zip(last.additions.solver_state, last2.additions.solver_state):
+        assert torch.equal(a[idx], b)
+    # against the oracle on the sample
+    ref = orc.sim_ahead(sub, acts[pick], orc.tau, orc.tau)
+    scales = field_scales(orc)
+    for name, b, s_ in zip(e.PHYS_FIELDS, ref["traj"], scales):
+        err = traj_err(np_(getattr(states2.physical_state, name)), b, s_)
+        assert err <= 1e-4, (name, err)
+    own = [np_(getattr(states.physical_state, n)) if n in ("i_d", "i_q") else None for n in e.PHYS_FIELDS]
+    assert np.array_equal(np_(trunc).astype(np.uint8), flags_from_states(orc, own))
+    assert bool(torch.isfinite(obs).all()) and bool((rew == 0).all())
+
+
 @pytest.mark.parametrize("layout", ["batch_major", "time_major"])
 @pytest.mark.parametrize("env,solver", [("mass_spring_damper", O.TSIT5), ("pendulum", O.EULER), ("pmsm", O.TSIT5)])
 def test_trajectory_kernels_write_only_their_outputs(excenvs, env, solver, layout):
