@@ -95,7 +95,7 @@ int launch_sim_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedu
 int launch_sim_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_f64(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
-// saturated PMSM, Tsit5, coefficient-form flux maps (exenv_simtm_pmsm_coef_f32.cu); plan.lut.coef must exist
+// saturated PMSM, coefficient-form flux maps (exenv_simtm_pmsm_coef_f32.cu); plan.lut.coef must exist
 int launch_simtm_pmsm_coef_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream);
 int launch_simtm_packed_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream,
                             int envs_per_thread);

@@ -640,7 +640,7 @@ static int simtm_dispatch2(const ExenvPlan &plan, const ExenvSimArgs &x, const S
                 : launch_simtm_w<Env, EXENV_EULER, T, false, true, 1>(plan, x, s, st);
 #if !defined(EXENV_SIMTM_COEF_TU)
   if constexpr (Env::IS_PMSM && Env::SATURATED && std::is_same<T, float>::value) {
-    if (tsit && simtm_coef_fits(plan)) return launch_simtm_pmsm_coef_f32(plan, x, s, st);  // exenv_simtm_pmsm_coef_f32.cu
+    if (simtm_coef_fits(plan)) return launch_simtm_pmsm_coef_f32(plan, x, s, st);  // exenv_simtm_pmsm_coef_f32.cu
   }
 #endif
   return tsit ? launch_simtm_fast<Env, EXENV_TSIT5, T>(plan, x, s, st) : launch_simtm_fast<Env, EXENV_EULER, T>(plan, x, s, st);
@@ -663,9 +663,10 @@ static int simtm_dispatch(const ExenvPlan &plan, const ExenvSimArgs &x, const Si
 }
 
 #if defined(EXENV_SIMTM_COEF_TU)
-// Tsit5 trajectories of the saturated PMSM with coefficient-form flux maps, with and without the fused epilogue
+// trajectories of the saturated PMSM with coefficient-form flux maps, with and without the fused epilogue
 int launch_simtm_pmsm_coef_f32(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch, cudaStream_t stream) {
-  return launch_simtm_fast<Pmsm<float, 2>, EXENV_TSIT5, float>(plan, a, sch, stream);
+  if (plan.desc.solver == EXENV_TSIT5) return launch_simtm_fast<Pmsm<float, 2>, EXENV_TSIT5, float>(plan, a, sch, stream);
+  return launch_simtm_fast<Pmsm<float, 2>, EXENV_EULER, float>(plan, a, sch, stream);
 }
 #else
 int EXENV_CAT(launch_simtm_, EXENV_SFX)(const ExenvPlan &plan, const ExenvSimArgs &a, const SimSchedule &sch,

@@ -502,15 +502,17 @@ def test_persistent_pmsm_kernel_job_mapping(excenvs, motor):
 
 
 @pytest.mark.parametrize("layout", ["batch_major", "time_major"])
-@pytest.mark.parametrize("env,solver", [("mass_spring_damper", O.TSIT5), ("pendulum", O.EULER), ("pmsm", O.TSIT5)])
+@pytest.mark.parametrize("env,solver", [("mass_spring_damper", O.TSIT5), ("pendulum", O.EULER), ("pmsm", O.TSIT5),
+                                        ("pmsm_brusa_sat", O.TSIT5)])
 def test_trajectory_kernels_write_only_their_outputs(excenvs, env, solver, layout):
     """Guard zones around every output buffer stay untouched (ragged batches, every envs-per-thread width, the first
-    step's double save, the L2 prefetch running ahead of the action stream near its end)."""
+    step's double save, the L2 prefetch running ahead of the action stream near its end; the saturated PMSM runs the
+    persistent coefficient-form kernel in the time-major layout: jobs per warp, surplus lanes of the last job)."""
     rng = np.random.default_rng(31)
-    orc = O.Oracle(env, solver=solver, dtype=np.float32)
+    orc = _orc(env, solver, np.float32)
     G = 256  # guard floats on either side
     for B, T in ((388, 37), (390, 5), (129, 1), (4 * 1024, 9)):
-        st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=(env == "pmsm"))
+        st = random_state(orc, B, rng, spread=0.5, pmsm_gentle=(orc.env == "pmsm"))
         acts = torch.as_tensor(rng.uniform(-1, 1, (B, T, orc.A)).astype(np.float32), device="cuda") * 0.05
         e = make_env(excenvs, orc, B)
         NS, OW, D = T + 1, e.obs_dim, e.physical_state_dim
