@@ -162,13 +162,9 @@ __global__ void __launch_bounds__(SIMTM_THREADS, packed_min_blocks<Env, V>())
 
   // ---- saves: stash the step's first save per pair, one vector store per leaf / observation group afterwards -----
   const unsigned Bu = (unsigned)a.B;
-  T *tp[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) tp[d] = a.traj[d] + b;
-  T *op = a.obs + b * O;
-  T *rwp = EPI ? a.reward + b : nullptr;
-  uint8_t *trp = EPI ? a.trunc + b * NT0 : nullptr;
-  uint8_t *tmp = EPI ? a.term + b : nullptr;
+  // one running element index (save step_first_save, environment b) of an (N+1, B) array addresses every output; the
+  // addresses are formed from the kernel-argument base pointers at the store (exenv_simtm.inl)
+  size_t srow = (size_t)b;
   P stash[VV][NST];
   long step_first_save = 0;
   auto observe_pair = [&](const P *sv, P *ob) {
@@ -198,26 +194,25 @@ __global__ void __launch_bounds__(SIMTM_THREADS, packed_min_blocks<Env, V>())
       observe_pair(svp, obp);
 #pragma unroll
       for (int l = 0; l < 2; ++l) {
-        const size_t roff = (size_t)(sidx - step_first_save) * Bu + 2 * vv + l;
+        const size_t row = srow + (size_t)(sidx - step_first_save) * Bu + 2 * vv + l;
         T sv[D], ob[O];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           sv[d] = l ? svp[d].y : svp[d].x;
-          __stcs(tp[d] + roff, sv[d]);
+          __stcs(a.traj[d] + row, sv[d]);
         }
 #pragma unroll
         for (int o = 0; o < O; ++o) {
           ob[o] = l ? obp[o].y : obp[o].x;
-          __stcs(op + roff * O + o, ob[o]);
+          __stcs(a.obs + row * O + o, ob[o]);
         }
         if constexpr (EPI) {
           uint8_t tr[NT0], te;
           flags_lane(sv, ob, tr, te);
 #pragma unroll
-          for (int i = 0; i < NT0; ++i) trp[roff * NT0 + i] = tr[i];
-          const size_t r1 = (size_t)(sidx - step_first_save - (step_first_save == 0 ? 1 : 0)) * Bu + 2 * vv + l;
-          __stcs(rwp + r1, (T)0);
-          tmp[r1] = te;
+          for (int i = 0; i < NT0; ++i) a.trunc[row * NT0 + i] = tr[i];
+          __stcs(a.reward + (row - Bu), (T)0);  // rows of states[1:]: one behind (sidx >= 1 here)
+          a.term[row - Bu] = te;
         }
       }
     }
@@ -245,11 +240,9 @@ __global__ void __launch_bounds__(SIMTM_THREADS, packed_min_blocks<Env, V>())
       T col[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) col[v] = sv[v][d];
-      store_vec<T, V>(tp[d], col);
-      tp[d] += (size_t)Bu * (unsigned)ns;
+      store_vec<T, V>(a.traj[d] + srow, col);
     }
-    store_vec<T, V * O>(op, &ob[0][0]);
-    op += (size_t)Bu * (unsigned)(ns * O);
+    store_vec<T, V * O>(a.obs + srow * O, &ob[0][0]);
     if constexpr (EPI) {
       uint8_t tr[V][NT0], te[V];
       T zero[V];
@@ -258,16 +251,13 @@ __global__ void __launch_bounds__(SIMTM_THREADS, packed_min_blocks<Env, V>())
         flags_lane(sv[v], ob[v], tr[v], te[v]);
         zero[v] = (T)0;
       }
-      store_vec<uint8_t, V * NT0>(trp, &tr[0][0]);
-      trp += (size_t)Bu * (unsigned)(ns * NT0);
-      if (step_first_save > 0) {
-        store_vec<T, V>(rwp, zero);
-        store_vec<uint8_t, V>(tmp, te);
+      store_vec<uint8_t, V * NT0>(a.trunc + srow * NT0, &tr[0][0]);
+      if (step_first_save > 0) {  // save 0 has no reward / terminated entry
+        store_vec<T, V>(a.reward + (srow - Bu), zero);
+        store_vec<uint8_t, V>(a.term + (srow - Bu), te);
       }
-      const unsigned adv = (unsigned)(step_first_save > 0 ? ns : ns - 1);
-      rwp += (size_t)Bu * adv;
-      tmp += (size_t)Bu * adv;
     }
+    srow += (size_t)Bu * (unsigned)ns;
   };
 
   // ---- the solver loop (schedule records from this warp's shared-memory copy, see exenv_simtm_common.cuh) ---------
