@@ -234,6 +234,8 @@ int hc_lut_forms(long n, const double *gx, const double *gy, const double *maps,
   }
   return exact ? 1 : 0;
 }
+// exenv_envs.cuh: does a grid qualify for the coefficient form (nodes == fl(g0 + i * d) exactly in float32)?
+int hc_lut_grid_exact(const double *g, int n) { return lut_grid_exact_f32(g, n) ? 1 : 0; }
 void hc_fmod_two_pi(long n, int is_f64, const void *x, void *fmod_out, void *wrap_out) {
   for (long i = 0; i < n; ++i) {
     if (is_f64) {

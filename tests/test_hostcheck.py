@@ -308,3 +308,22 @@ def test_flux_map_coefficient_form(hostcheck_lib, motor):
     assert ec.max() <= 1e-6, ec.max()
     assert ec.max() <= 4 * en.max() + 1e-7, (ec.max(), en.max())
     assert np.array_equal(dyc[:, 2], om) and np.array_equal(dyn[:, 2], om)
+
+
+def test_coefficient_form_is_only_built_for_exactly_representable_grids(hostcheck_lib):
+    """exenv_envs.cuh: lut_grid_exact_f32 -- the coefficient-form kernel rebuilds cell origins as g0 + i * d in float32,
+    so plans get that table only for grids where this is exact; everything else keeps the node form with its per-cell
+    origin / width reads."""
+    f = hostcheck_lib.hc_lut_grid_exact
+    f.restype = C.c_int
+
+    def ok(g):
+        g = np.ascontiguousarray(g, np.float64)
+        return f(C.c_void_p(g.ctypes.data), C.c_int(g.size)) == 1
+
+    assert ok(np.arange(-260.0, 261.0, 10.0)) and ok(np.arange(-17.0, 18.0, 1.0)) and ok(np.arange(0, 8) * 0.25 - 3.5)
+    assert not ok(np.arange(0, 50) * 0.1)                      # 0.1 is not a float32 number
+    assert not ok(np.array([0.0, 1.0, 2.0, 3.5, 4.0]))         # not equidistant
+    assert not ok(np.array([0.0, 1.0, 2.0, 3.0 + 1e-9]))       # equidistant only up to rounding
+    assert not ok(np.arange(0, 40) * 1.0 + 2.0 ** 25)          # nodes beyond the float32 integer range
+    assert not ok(np.array([3.0])) and not ok(np.array([2.0, 1.0, 0.0]))
