@@ -367,17 +367,8 @@ EX_HD float f32_from_bits(int i) {
 // (two selects and two sign flips) per lane: ~16 packed + ~12 scalar instructions for two angles, against ~25 scalar
 // instructions per angle for CUDA's sincosf.  Maximum error 1.6 ulp for |x| < 1e5 (tests/test_hostcheck.py; CUDA's
 // sinf / cosf: 1.5 ulp); larger arguments, inf and nan take libm per lane.
-#if defined(__CUDACC__)
-// Large arguments (|x| >= 1e5), inf, nan: libm per lane.  Out of line: the Payne-Hanek reduction of sincosf is a few
-// hundred instructions, and sincos2 is inlined 7-14 times per solver step -- inline, these never-executed blocks made
-// the step bodies of the pendulum / cart-pole / acrobot kernels 70-140 KB, several times the instruction cache.
-static __device__ __noinline__ float4 sincos2_slow(float x, float y, float4 fast) {
-  if (!(::fabsf(x) < 100000.0f)) ::sincosf(x, &fast.x, &fast.z);
-  if (!(::fabsf(y) < 100000.0f)) ::sincosf(y, &fast.y, &fast.w);
-  return fast;  // {sin x, sin y, cos x, cos y}
-}
-#endif
-EX_HD void sincos2(f32x2 x, f32x2 *sn, f32x2 *cs) {
+// The polynomial path alone (every argument; garbage beyond the reduction's range).
+EX_HD void sincos2_poly(f32x2 x, f32x2 *sn, f32x2 *cs) {
   const f32x2 kf = fma_(x, f32x2(0.63661977236758134f), f32x2(12582912.0f));
   const f32x2 k = kf + f32x2(-12582912.0f);
   f32x2 r = fma_(k, f32x2(-1.5707963705062866f), x);
@@ -398,12 +389,29 @@ EX_HD void sincos2(f32x2 x, f32x2 *sn, f32x2 *cs) {
   };
   lane(kf.x, s.x, c.x, &sn->x, &cs->x);
   lane(kf.y, s.y, c.y, &sn->y, &cs->y);
+}
+#if defined(__CUDACC__)
+// Large arguments (|x| >= 1e5), inf, nan: libm per lane.  Out of line: the Payne-Hanek reduction of sincosf is a few
+// hundred instructions, and sincos2 is inlined 7-14 times per solver step -- inline, these never-executed blocks made
+// the step bodies of the pendulum / cart-pole / acrobot kernels 70-140 KB, several times the instruction cache.  Takes
+// the two angles only (two argument registers to set up at every call site) and redoes the polynomial path for a lane
+// that is in range: the same operations, the same value.
+static __device__ __noinline__ float4 sincos2_slow(float x, float y) {
+  f32x2 s, c;
+  sincos2_poly(f32x2(x, y), &s, &c);
+  if (!(::fabsf(x) < 100000.0f)) ::sincosf(x, &s.x, &c.x);
+  if (!(::fabsf(y) < 100000.0f)) ::sincosf(y, &s.y, &c.y);
+  return make_float4(s.x, s.y, c.x, c.y);
+}
+#endif
+EX_HD void sincos2(f32x2 x, f32x2 *sn, f32x2 *cs) {
+  sincos2_poly(x, sn, cs);
   // beyond the reduction's range (or inf / nan): libm, per lane.  One warp-wide vote decides whether anybody has to go
   // there, so that the common case costs a uniform branch instead of four divergent ones.
   const bool big = !(::fabsf(x.x) < 100000.0f) || !(::fabsf(x.y) < 100000.0f);
 #if defined(__CUDA_ARCH__)
   if (__any_sync(__activemask(), big)) {
-    const float4 r = sincos2_slow(x.x, x.y, make_float4(sn->x, sn->y, cs->x, cs->y));
+    const float4 r = sincos2_slow(x.x, x.y);
     sn->x = r.x;
     sn->y = r.y;
     cs->x = r.z;
