@@ -2,6 +2,7 @@
 // Nothing here touches memory; every function is a pure scalar transform so that the same source is
 // compiled by nvcc for sm_100a (product) and by g++ for tests/hostcheck (device-math host harness).
 #pragma once
+#include <type_traits>
 
 #include <cmath>
 #include <cstdint>
@@ -517,6 +518,27 @@ EX_HD f32x2 sign_of<f32x2>(f32x2 v) {
 }
 #endif
 
+// Tableau coefficients a_ij (row-major below the diagonal; row 7 = the solution weights b_j).  fp32 / packed fp32: literals
+// (32-bit immediates of FFMA / FFMA2).  fp64 on the device: a __constant__ table -- DFMA takes a constant-bank operand but
+// no 64-bit immediate, and as literals the 21 coefficients cost two moves each per solver step (88 of the 267 warp
+// instructions per env-step of the fp64 mass-spring-damper trajectory kernel, profiles/README.md).
+#define EXENV_TSIT5_A                                                                                                 \
+  {0.161, -0.008480655492356989, 0.335480655492357, 2.8971530571054935, -6.359448489975075, 4.3622954328695815,       \
+   5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 5.86145544294642,                \
+   -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0.09646076681806523, 0.01,       \
+   0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}
+#if defined(__CUDACC__)
+static __constant__ double k_tsit5_a_f64[21] = EXENV_TSIT5_A;
+#endif
+template <typename T>
+EX_HD T tsit5_a(int i) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (std::is_same<T, double>::value) return k_tsit5_a_f64[i];
+#endif
+  constexpr double v[21] = EXENV_TSIT5_A;
+  return (T)v[i];
+}
+
 // ---- Tsit5 (diffrax.Tsit5; Tsitouras 2011).  SURVEY Appendix B.2 --------------------------------------------
 // Stage increments are k_i = f_i * dt (diffrax "vf_prod"); stage states y0 + sum_j a_ij k_j; the solution is the
 // stage-7 state (FSAL/SSAL tableau).  `rhs(stage, y, f)` evaluates the vector field for stage index 1..6
@@ -524,15 +546,13 @@ EX_HD f32x2 sign_of<f32x2>(f32x2 v) {
 // k[0..6][N] are returned for dense output; f_last = f(t0 + dt, y1).
 template <typename T, int N, class F>
 EX_HD void tsit5_step(const T *y0, const T *f0, T dt, F &&rhs, T *y1, T *f_last, T (*k)[N]) {
-  constexpr T a21 = (T)0.161;
-  constexpr T a31 = (T)-0.008480655492356989, a32 = (T)0.335480655492357;
-  constexpr T a41 = (T)2.8971530571054935, a42 = (T)-6.359448489975075, a43 = (T)4.3622954328695815;
-  constexpr T a51 = (T)5.325864828439257, a52 = (T)-11.748883564062828, a53 = (T)7.4955393428898365,
-              a54 = (T)-0.09249506636175525;
-  constexpr T a61 = (T)5.86145544294642, a62 = (T)-12.92096931784711, a63 = (T)8.159367898576159,
-              a64 = (T)-0.071584973281401, a65 = (T)-0.028269050394068383;
-  constexpr T a71 = (T)0.09646076681806523, a72 = (T)0.01, a73 = (T)0.4798896504144996,
-              a74 = (T)1.379008574103742, a75 = (T)-3.290069515436081, a76 = (T)2.324710524099774;
+  const T a21 = tsit5_a<T>(0);
+  const T a31 = tsit5_a<T>(1), a32 = tsit5_a<T>(2);
+  const T a41 = tsit5_a<T>(3), a42 = tsit5_a<T>(4), a43 = tsit5_a<T>(5);
+  const T a51 = tsit5_a<T>(6), a52 = tsit5_a<T>(7), a53 = tsit5_a<T>(8), a54 = tsit5_a<T>(9);
+  const T a61 = tsit5_a<T>(10), a62 = tsit5_a<T>(11), a63 = tsit5_a<T>(12), a64 = tsit5_a<T>(13), a65 = tsit5_a<T>(14);
+  const T a71 = tsit5_a<T>(15), a72 = tsit5_a<T>(16), a73 = tsit5_a<T>(17), a74 = tsit5_a<T>(18), a75 = tsit5_a<T>(19),
+          a76 = tsit5_a<T>(20);
   T ys[N], f[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) k[0][i] = f0[i] * dt;
@@ -583,15 +603,13 @@ EX_HD void tsit5_step(const T *y0, const T *f0, T dt, F &&rhs, T *y1, T *f_last,
 //   f[0][.] = FSAL derivative at (t0, y0) on entry; f[1..6][.] are filled; f[6] = f(t0 + dt, y1).
 template <typename T, int N, class F>
 EX_HD void tsit5_step_f(const T *y0, T dt, F &&rhs, T *y1, T (*f)[N]) {
-  constexpr T a21 = (T)0.161;
-  constexpr T a31 = (T)-0.008480655492356989, a32 = (T)0.335480655492357;
-  constexpr T a41 = (T)2.8971530571054935, a42 = (T)-6.359448489975075, a43 = (T)4.3622954328695815;
-  constexpr T a51 = (T)5.325864828439257, a52 = (T)-11.748883564062828, a53 = (T)7.4955393428898365,
-              a54 = (T)-0.09249506636175525;
-  constexpr T a61 = (T)5.86145544294642, a62 = (T)-12.92096931784711, a63 = (T)8.159367898576159,
-              a64 = (T)-0.071584973281401, a65 = (T)-0.028269050394068383;
-  constexpr T a71 = (T)0.09646076681806523, a72 = (T)0.01, a73 = (T)0.4798896504144996,
-              a74 = (T)1.379008574103742, a75 = (T)-3.290069515436081, a76 = (T)2.324710524099774;
+  const T a21 = tsit5_a<T>(0);
+  const T a31 = tsit5_a<T>(1), a32 = tsit5_a<T>(2);
+  const T a41 = tsit5_a<T>(3), a42 = tsit5_a<T>(4), a43 = tsit5_a<T>(5);
+  const T a51 = tsit5_a<T>(6), a52 = tsit5_a<T>(7), a53 = tsit5_a<T>(8), a54 = tsit5_a<T>(9);
+  const T a61 = tsit5_a<T>(10), a62 = tsit5_a<T>(11), a63 = tsit5_a<T>(12), a64 = tsit5_a<T>(13), a65 = tsit5_a<T>(14);
+  const T a71 = tsit5_a<T>(15), a72 = tsit5_a<T>(16), a73 = tsit5_a<T>(17), a74 = tsit5_a<T>(18), a75 = tsit5_a<T>(19),
+          a76 = tsit5_a<T>(20);
   T ys[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) ys[i] = fma_(dt, a21 * f[0][i], y0[i]);
