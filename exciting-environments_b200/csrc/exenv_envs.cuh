@@ -387,11 +387,15 @@ struct CartPole {
   using Aux = NoAux;
   struct Pre {
     InvDiv<T> M, mpl;
+    T k_mup, l43, lmM;  // FAST form: mu_p / (m_p l), 4 l / 3, l m_p / M
   };
   EX_HD static Pre precompute(const T *p) {
     Pre q;
     q.M = make_invdiv<T>(p[4] + p[3]);
     q.mpl = make_invdiv<T>(p[3] * p[2]);
+    q.k_mup = p[0] / (p[3] * p[2]);
+    q.l43 = p[2] * (T)(4.0 / 3.0);
+    q.lmM = p[2] * p[3] / (p[4] + p[3]);
     return q;
   }
   // :159-180  p = mu_p, mu_c, l, m_p, m_c, g ; y = deflection, velocity, theta, omega
@@ -405,9 +409,11 @@ struct CartPole {
     T d_om, d_v;
     if constexpr (FAST) {  // quotients by parameters as products with the prepared reciprocal, the one state-dependent
                            // division as a Newton-refined reciprocal (exenv_math.cuh: div_mul, rcp_nr)
-      d_om = (g * s + c * div_mul<T>(-u[0] - q.mpl.d * (om * om) * s + mu_c * sg, q.M) - div_mul<T>(mu_p * om, q.mpl)) *
-             rcp_nr(l * ((T)(4.0 / 3.0) - div_mul<T>(m_p * (c * c), q.M)));
-      d_v = div_mul<T>(u[0] + q.mpl.d * ((om * om) * s - d_om * c) - mu_c * sg, q.M);
+      // (the denominator l (4/3 - m_p c^2 / M) and the friction quotient with constants prepared in Pre)
+      const T ws = (om * om) * s, fr = mu_c * sg;
+      d_om = fma_(-q.k_mup, om, fma_(c, div_mul<T>(fma_(-q.mpl.d, ws, fr - u[0]), q.M), g * s)) *
+             rcp_nr(fma_(-q.lmM, c * c, q.l43));
+      d_v = div_mul<T>(fma_(q.mpl.d, fma_(-d_om, c, ws), u[0] - fr), q.M);
     } else {
       d_om = (g * s + c * div_inv<false, T>(-u[0] - q.mpl.d * (om * om) * s + mu_c * sg, q.M) -
               div_inv<false, T>(mu_p * om, q.mpl)) /
@@ -436,46 +442,75 @@ struct Acrobot {
   static constexpr bool IS_PMSM = false, SATURATED = false;
   using Aux = NoAux;
   // :171-197  p = g, l_1, l_2, m_1, m_2, l_c1, l_c2, I_1, I_2 ; y = theta_1, theta_2, omega_1, omega_2
-  struct Pre {};
-  EX_HD static Pre precompute(const T *) { return Pre{}; }
+  // Parameter-only products of the right-hand side (FAST form): d11 = A0 + 2 c1 cos(theta_2), d12 = A1 + c1 cos(theta_2),
+  // d22 = A1, h1 = -c1 sin(theta_2) omega_2 (omega_2 + 2 omega_1), h2 = c1 sin(theta_2) omega_1^2,
+  // phi1 = G1 ca + G2 cb, phi2 = G2 cb.
+  struct Pre {
+    T A0, A1, c1, c1x2, G1, G2;
+  };
+  EX_HD static Pre precompute(const T *p) {
+    const T g = p[0], l1 = p[1], m1 = p[3], m2 = p[4], lc1 = p[5], lc2 = p[6], I1 = p[7], I2 = p[8];
+    Pre q;
+    q.A0 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2) + I1 + I2;
+    q.A1 = m2 * (lc2 * lc2) + I2;
+    q.c1 = m2 * l1 * lc2;
+    q.c1x2 = (T)2 * q.c1;
+    q.G1 = (m1 * lc1 + m2 * l1) * g;
+    q.G2 = m2 * lc2 * g;
+    return q;
+  }
   template <class SrcPre>
-  EX_HD static Pre from_scalar(const SrcPre &) { return Pre{}; }
+  EX_HD static Pre from_scalar(const SrcPre &s) {
+    Pre q;
+    q.A0 = T(s.A0);
+    q.A1 = T(s.A1);
+    q.c1 = T(s.c1);
+    q.c1x2 = T(s.c1x2);
+    q.G1 = T(s.G1);
+    q.G2 = T(s.G2);
+    return q;
+  }
   template <typename U>
   using rebind = Acrobot<U>;
   template <bool FAST>
-  EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &, const Aux &, T *dy) {
-    const T g = p[0], l1 = p[1], m1 = p[3], m2 = p[4], lc1 = p[5], lc2 = p[6], I1 = p[7], I2 = p[8];
+  EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &q, const Aux &, T *dy) {
     const T th1 = y[0], th2 = y[1], om1 = y[2], om2 = y[3];
     T s2, c2;
     Mth<T>::sincos(th2, &s2, &c2);
+    if constexpr (FAST) {
+      // * everything that depends on parameters alone prepared once (Pre): ~45 -> ~15 operations for d11 ... phi2;
+      // * cos(x + pi/2) = -sin(x): one sincos of theta_1 and the angle-sum identity replace two cosines (the reference's
+      //   arguments carry the rounding of x + fl(pi/2), i.e. a few 1e-7 of noise in fp32; the values agree to that level);
+      // * three divisions by two state-dependent denominators -> two Newton-refined reciprocals (rcp_nr)
+      T s1, c1;
+      Mth<T>::sincos(th1, &s1, &c1);
+      const T ca = -s1, cb = -(s1 * c2 + c1 * s2);
+      const T d11 = fma_(q.c1x2, c2, q.A0), d12 = fma_(q.c1, c2, q.A1), d22 = q.A1;
+      const T cs = q.c1 * s2;
+      const T h1 = -(cs * om2) * fma_((T)2, om1, om2), h2 = cs * (om1 * om1);
+      const T phi2 = q.G2 * cb, phi1 = fma_(q.G1, ca, phi2);
+      const T r12 = rcp_nr(d12);
+      const T qq = d22 * r12;
+      const T d_om1 = rcp_nr(fma_(-qq, d11, d12)) * (fma_(qq, h1 + phi1, u[0]) - h2 - phi2);
+      dy[0] = om1;
+      dy[1] = om2;
+      dy[2] = d_om1;
+      dy[3] = -(fma_(d11, d_om1, h1) + phi1) * r12;
+      return;
+    }
+    // the reference's expressions, operation by operation (Euler in fp64: golden-vector replay)
+    const T g = p[0], l1 = p[1], m1 = p[3], m2 = p[4], lc1 = p[5], lc2 = p[6], I1 = p[7], I2 = p[8];
     const T d11 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2 + (T)2 * l1 * lc2 * c2) + I1 + I2;
     const T d12 = m2 * (lc2 * lc2 + l1 * lc2 * c2) + I2;
     const T d22 = m2 * (lc2 * lc2) + I2;
     const T h1 = -m2 * l1 * lc2 * s2 * (om2 * om2) - (T)2 * m2 * l1 * lc2 * s2 * om1 * om2;
     const T h2 = m2 * l1 * lc2 * s2 * (om1 * om1);
-    T ca, cb, d_om1, d_om2;
-    if constexpr (FAST) {  // cos(x + pi/2) = -sin(x): one sincos of theta_1 and the angle-sum identity replace two
-                           // cosines (the reference's arguments carry the rounding of x + fl(pi/2), i.e. a few 1e-7 of
-                           // noise in fp32; the values agree to that level)
-      T s1, c1;
-      Mth<T>::sincos(th1, &s1, &c1);
-      ca = -s1;
-      cb = -(s1 * c2 + c1 * s2);
-    } else {
-      ca = Mth<T>::cos(th1 + Cst<T>::half_pi());
-      cb = Mth<T>::cos(th1 + th2 + Cst<T>::half_pi());
-    }
+    const T ca = Mth<T>::cos(th1 + Cst<T>::half_pi());
+    const T cb = Mth<T>::cos(th1 + th2 + Cst<T>::half_pi());
     const T phi1 = (m1 * lc1 + m2 * l1) * g * ca + m2 * lc2 * g * cb;
     const T phi2 = m2 * lc2 * g * cb;
-    if constexpr (FAST) {  // three divisions by two state-dependent denominators -> two Newton-refined reciprocals
-      const T r12 = rcp_nr(d12);
-      const T qq = d22 * r12;
-      d_om1 = rcp_nr(d12 - qq * d11) * (u[0] + qq * (h1 + phi1) - h2 - phi2);
-      d_om2 = (-d11 * d_om1 - h1 - phi1) * r12;
-    } else {
-      d_om1 = (T)1 / (d12 - d22 / d12 * d11) * (u[0] + d22 / d12 * (h1 + phi1) - h2 - phi2);
-      d_om2 = (-d11 * d_om1 - h1 - phi1) / d12;
-    }
+    const T d_om1 = (T)1 / (d12 - d22 / d12 * d11) * (u[0] + d22 / d12 * (h1 + phi1) - h2 - phi2);
+    const T d_om2 = (-d11 * d_om1 - h1 - phi1) / d12;
     dy[0] = om1;
     dy[1] = om2;
     dy[2] = d_om1;

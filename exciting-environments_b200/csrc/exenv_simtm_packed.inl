@@ -15,12 +15,14 @@
 // action q + 2 in flight.  Every regular step reads at most two consecutive indices and advances q by 0 or 1; the rare
 // steps that touch 3-4 indices or jump further (the accumulated fp32 solver time produces a handful per trajectory)
 // take a second copy of the step body that loads its actions straight from global memory.
-// Resident CTAs per SM the register allocation aims at: two-component systems keep four environments per thread in 128
-// registers; the four-component ones (cart-pole, acrobot: seven stage derivatives of four packed components = 56
-// registers per pair) need ~160 registers for one pair per thread.
+// Resident CTAs per SM the register allocation aims at: 128 registers for four environments per thread of the
+// two-component systems and for ONE PAIR per thread of the four-component ones (cart-pole, acrobot: seven stage
+// derivatives of four packed components = 56 registers per pair; with the parameter-only products of their right-hand
+// sides prepared on the host the acrobot fits without a spill, the cart-pole with 32-56 bytes -- four CTAs per SM
+// instead of three: +5 % / +4 %, profiles/README.md); two pairs per thread of those: two CTAs.
 template <class Env, int V>
 constexpr int packed_min_blocks() {
-  return Env::NODE >= 4 ? (V == 4 ? 2 : 3) : (V == 4 ? 4 : 5);
+  return Env::NODE >= 4 ? (V == 4 ? 2 : 4) : (V == 4 ? 4 : 5);
 }
 // Solver steps per trip of the step loop: two for the mass-spring-damper (its loop-carried state then ping-pongs
 // between two register sets instead of being copied back after every step: 44 MOVs per thread-step); one for the
