@@ -398,6 +398,18 @@ struct CartPole {
     q.lmM = p[2] * p[3] / (p[4] + p[3]);
     return q;
   }
+  template <class SrcPre>
+  EX_HD static Pre from_scalar(const SrcPre &s) {  // scalar -> packed: splats that stay broadcast operands
+    Pre q;
+    q.M.d = T(s.M.d);
+    q.M.r = T(s.M.r);
+    q.mpl.d = T(s.mpl.d);
+    q.mpl.r = T(s.mpl.r);
+    q.k_mup = T(s.k_mup);
+    q.l43 = T(s.l43);
+    q.lmM = T(s.lmM);
+    return q;
+  }
   // :159-180  p = mu_p, mu_c, l, m_p, m_c, g ; y = deflection, velocity, theta, omega
   template <bool FAST>
   EX_HD static void rhs(const T *y, const T *u, const T *p, const Pre &q, const Aux &, T *dy) {

@@ -278,7 +278,7 @@ __device__ __forceinline__ void staged_to_fields(const T *st, T omega_el, T *sv)
 // The bandwidth-bound Euler kernels lose 2-3 % as well: Tsit5 only.
 template <class Env, int SOLVER>
 constexpr bool simtm_use_host_pre() {
-  return SOLVER == EXENV_TSIT5 && (Env::ID == 1 || Env::ID == 4 || Env::ID == 5);
+  return SOLVER == EXENV_TSIT5 && (Env::ID == 1 || Env::ID == 3 || Env::ID == 4 || Env::ID == 5);
 }
 template <class Env, typename T>
 struct SimTmHostPre {
