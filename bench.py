@@ -215,6 +215,10 @@ class NvmlClockSampler:
             f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
         self.rows, self.stop_flag = [], False
         self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        try:
+            self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+        except Exception:
+            self.power_limit_w = None
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
 
@@ -225,7 +229,11 @@ class NvmlClockSampler:
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.rows.append((time.time(), float(mhz), pw, int(rs)))
+                try:
+                    mem = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
+                except Exception:
+                    mem = 0.0
+                self.rows.append((time.time(), float(mhz), pw, int(rs), mem))
             except Exception:
                 pass
             time.sleep(0.02)
@@ -236,6 +244,8 @@ class NvmlClockSampler:
         self.stop_flag = True
         self.t.join(timeout=2)
         out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "how": "NVML thread, 20 ms"}
+        if self.power_limit_w:
+            out["power_limit_w"] = self.power_limit_w
         inside = [r for r in self.rows if t0 is not None and t0 - 0.01 <= r[0] <= t1 + 0.01]
         window = "timed region"
         if not inside:
@@ -244,6 +254,9 @@ class NvmlClockSampler:
             sm = sorted(r[1] for r in inside)
             out.update(sm_mhz=sm[len(sm) // 2], sm_mhz_min=sm[0], samples=len(sm), window=window,
                        power_w_max=max(r[2] for r in inside))
+            mem = sorted(r[4] for r in inside if len(r) > 4 and r[4] > 0)
+            if mem:
+                out.update(mem_mhz=mem[len(mem) // 2], mem_mhz_min=mem[0])
             bits = 0
             for r in inside:
                 bits |= r[3]
